@@ -1,0 +1,67 @@
+"""Deterministic synthetic single-cell trajectories.
+
+Used by ``bench.py``, the tests and the golden-fixture script: there is no network for
+real datasets, so every measured shape is generated from seeds.  Values are
+``log1p``-normalised float32 like the reference's bundled ``.h5ad`` inputs.
+"""
+import numpy as np
+
+__all__ = ["CONFIGS", "gene_params", "make_side", "make_pair"]
+
+# name -> (n_genes, n_ref_cells, n_query_cells, n_interpolation_points)   BASELINE.json "configs"
+CONFIGS = {
+    "C1": (89, 179, 290, 14),
+    "C2": (1371, 20327, 17176, 14),
+    "C3": (994, 3157, 890, 13),
+    "C4": (20000, 100000, 100000, 50),
+    "C5": (30000, 1000000, 1000000, 100),
+}
+
+
+def gene_params(n_genes, seed=0):
+    """Per-gene bump parameters shared by the reference and the query side."""
+    rng = np.random.default_rng(seed)
+    return {
+        "amp": rng.uniform(0.5, 3.0, n_genes),
+        "ph": rng.uniform(0.0, 1.0, n_genes),
+        "w": rng.uniform(0.1, 0.5, n_genes),
+        # ~1% silent on ref only, ~1% on query only, ~1% on both (hits Main.py:344-374)
+        "silent": rng.choice(4, size=n_genes, p=[0.97, 0.01, 0.01, 0.01]),
+    }
+
+
+def make_side(n_cells, params, seed, side, dropout=0.6, shift=0.0, row_chunk=8192, out=None):
+    """One dataset: returns (X float32 [n_cells, n_genes], time float64 [n_cells]).
+
+    ``side`` is 0 for the reference, 1 for the query (selects which genes are silent);
+    ``shift`` moves every bump along pseudotime so ref and query differ.
+    """
+    rng = np.random.default_rng(seed)
+    n_genes = len(params["amp"])
+    tau = rng.uniform(0.0, 1.0, n_cells)
+    tau = (tau - tau.min()) / (tau.max() - tau.min())  # exactly [0, 1]
+    X = out if out is not None else np.empty((n_cells, n_genes), dtype=np.float32)
+    silent = params["silent"]
+    dead = (silent == 3) | (silent == (1 if side == 0 else 2))
+    amp = params["amp"][None, :]
+    ph = params["ph"][None, :] + shift
+    w = params["w"][None, :]
+    for r0 in range(0, n_cells, row_chunk):
+        r1 = min(n_cells, r0 + row_chunk)
+        t = tau[r0:r1, None]
+        signal = amp * np.exp(-((t - ph) / w) ** 2)
+        val = signal + rng.normal(0.0, 0.3, signal.shape)
+        np.maximum(val, 0.0, out=val)
+        drop = rng.uniform(0.0, 1.0, signal.shape) < dropout * np.exp(-signal)
+        val[drop] = 0.0
+        val[:, dead] = 0.0
+        X[r0:r1] = np.log1p(val).astype(np.float32)
+    return X, tau
+
+
+def make_pair(n_genes, n_ref, n_query, dropout=0.6, seed=0):
+    """(X_ref, time_ref, X_query, time_query, gene_names) with seeds 1 (ref) / 2 (query)."""
+    params = gene_params(n_genes, seed)
+    Xr, tr = make_side(n_ref, params, 1, 0, dropout=dropout)
+    Xq, tq = make_side(n_query, params, 2, 1, dropout=dropout, shift=0.08)
+    return Xr, tr, Xq, tq, ["g%d" % i for i in range(n_genes)]
