@@ -1,0 +1,373 @@
+"""bench.py -- gene alignments / second of the Genes2Genes hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
+
+One "step" = one pass of the hot path over one batch: interpolation of every gene of the workload
+(K0 weights, K1a pilot, K1 moments, K3 fix-up) + cost/DP/traceback (K4) (+ the NCCL gather of the
+per-gene result records to rank 0 when N > 1).  Workload at N=1: BASELINE.json configs[1]
+("C2": 1371 genes, 20,327 ref / 17,176 query cells, 14 interpolation points), synthetic data of that
+shape (genes2genes_b200/synthetic.py).  For N > 1 every rank aligns its own C2-sized gene shard
+(weak scaling; genes are independent).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM);
+`e2e` is the same metric through the public API (`Main.RefQueryAligner(...)` + `align_all_pairs()`)
+from pinned host buffers, with the host->device copies and the device->host result read inside
+the timed region.  `--impl reference` times the CPU port of the reference algorithm
+(oracle/g2g_oracle.py, per-gene loop like Main.py:449-455) on all host cores instead.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "gene_alignments_per_sec"
+UNIT = "genes/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--dropout", type=float, default=0.9)
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-genes", type=int, default=512, help="genes in the bounded CPU-baseline sample")
+    return ap.parse_args()
+
+
+def workload(name, dropout, rank=0):
+    from genes2genes_b200 import synthetic
+    G, nr, nq, T = synthetic.CONFIGS[name]
+    Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=dropout, seed=100 + rank)
+    return Xr, tr, Xq, tq, genes, T
+
+
+def config_dict(name, dropout, n_gpus, extra=None):
+    from genes2genes_b200 import synthetic
+    G, nr, nq, T = synthetic.CONFIGS[name]
+    cfg = {"workload": "%s: %d genes x (%d ref + %d query cells), %d interpolation points, dense f32 [cells x genes], "
+                       "synthetic log1p counts with %.0f%% dropout" % (name, G, nr, nq, T, dropout * 100),
+           "genes_per_gpu": G, "n_ref_cells": nr, "n_query_cells": nq, "n_interpolation_points": T,
+           "parallelism": "genes sharded over %d GPU(s), final NCCL gather to rank 0" % n_gpus if n_gpus > 1
+           else "single GPU", "l2": "L2 flushed (256 MiB write) between timed steps"}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port, one gene at a time like the reference's loop (Main.py:449-455)
+# ---------------------------------------------------------------------------------------------------
+_CPU = {}
+
+
+def _cpu_init(Xr, Xq, tr, tq, T):
+    from oracle import g2g_oracle as o
+    orr, oq = o.sort_cells(tr), o.sort_cells(tq)
+    _CPU.update(o=o, Xr=Xr[orr], Xq=Xq[oq], taur=tr[orr], tauq=tq[oq], eps=o.epsilon_table(T),
+                Wr=o.weight_matrix(tr[orr], T), Wq=o.weight_matrix(tq[oq], T))
+
+
+def _cpu_gene(g):
+    c = _CPU
+    r = c["o"].align_gene_faithful(c["Xr"][:, g].astype(np.float64), c["Xq"][:, g].astype(np.float64), c["taur"],
+                                   c["tauq"], c["Wr"], c["Wq"], c["eps"])
+    return r["alignment_str"]
+
+
+def _one_blas_thread():
+    """Worker initialiser: one BLAS/OpenMP thread per process (the pool provides the parallelism)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["_limit"] = threadpool_limits(1)
+    except Exception:
+        pass
+
+
+def cpu_port_rate(Xr, tr, Xq, tq, T, n_genes, n_procs):
+    """genes/s of the oracle port on `n_genes` genes of the workload with `n_procs` processes."""
+    sel = np.arange(min(n_genes, Xr.shape[1]))
+    Xr_s, Xq_s = np.ascontiguousarray(Xr[:, sel]), np.ascontiguousarray(Xq[:, sel])
+    if n_procs <= 1:
+        _cpu_init(Xr_s, Xq_s, tr, tq, T)
+        _one_blas_thread()
+        t0 = time.perf_counter()
+        for g in range(len(sel)):
+            _cpu_gene(g)
+        return len(sel) / (time.perf_counter() - t0)
+    import multiprocessing as mp
+    ctx = mp.get_context("fork")
+    _cpu_init(Xr_s, Xq_s, tr, tq, T)  # inherited by the forked workers
+    with ctx.Pool(n_procs, initializer=_one_blas_thread) as pool:
+        pool.map(_cpu_gene, range(min(n_procs, len(sel))))  # spin the workers up
+        t0 = time.perf_counter()
+        pool.map(_cpu_gene, range(len(sel)), chunksize=max(1, len(sel) // (4 * n_procs)))
+        dt = time.perf_counter() - t0
+    return len(sel) / dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    Xr, tr, Xq, tq, genes, T = workload(args.workload, args.dropout)
+    cores = os.cpu_count() or 1
+    n_genes = min(Xr.shape[1], max(args.cpu_genes, 64 * cores))
+    rates = []
+    for _ in range(max(1, args.warmup > 0)):
+        cpu_port_rate(Xr, tr, Xq, tq, T, min(n_genes, 2 * cores), cores)
+    t0 = time.perf_counter()
+    for _ in range(max(1, min(args.steps, 3))):
+        rates.append(cpu_port_rate(Xr, tr, Xq, tq, T, n_genes, cores))
+    wall = time.perf_counter() - t0
+    rate = float(np.mean(rates))
+    sample = "%d genes of the workload at full cell counts per step, %d worker processes (fork)" % (n_genes, cores)
+    line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(rates), "warmup": 1, "ms_per_step": 1e3 * wall / len(rates), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args.workload, args.dropout, args.gpus),
+            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload_name):
+    """DRAM bytes per K1 launch from the committed ncu capture of this workload, if any."""
+    path = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
+    try:
+        d = json.load(open(path))
+        return d.get(workload_name, {}).get("dram_bytes_per_launch")
+    except Exception:
+        return None
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    from genes2genes_b200 import Main, engine
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    Xr, tr, Xq, tq, genes, T = workload(args.workload, args.dropout, rank)
+    G = len(genes)
+
+    # ---- device-resident arm -----------------------------------------------------------------------
+    tir = TrajectoryInterpolator(tr, T, adaptive_kernel=False).run()
+    tiq = TrajectoryInterpolator(tq, T, adaptive_kernel=False).run()
+    Xrd = engine.pack_dense(Xr, tir.order, None, dev)
+    Xqd = engine.pack_dense(Xq, tiq.order, None, dev)
+    eng = engine.AlignmentEngine(Xrd, tir.cell_pseudotimes, Xqd, tiq.cell_pseudotimes, G, T,
+                                 tir.kernel_denominators(), tiq.kernel_denominators(), device=dev)
+    gather = None
+    if world > 1:
+        from genes2genes_b200 import distributed
+        gather = distributed.ResultGather(eng, dst=0)
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+                 for _ in range(args.steps)]
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        eng.run()
+        if gather is not None:
+            gather.run()
+
+    step()  # first run sets kernel attributes / loads modules
+    torch.cuda.synchronize()
+    graph = None
+    if not args.no_graph and world == 1:
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eng.run()
+            side.synchronize()
+            with torch.cuda.graph(graph, stream=side):
+                eng.run()
+        torch.cuda.current_stream().wait_stream(side)
+    for _ in range(args.warmup):
+        flush_buf.fill_(1)
+        graph.replay() if graph is not None else step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    torch.cuda.synchronize()
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush_buf.fill_(k & 0xFF)      # evict X and the partial sums from L2 (not timed)
+        starts[k].record()
+        if graph is not None:
+            graph.replay()
+        else:
+            step()
+        ends[k].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    wall = time.perf_counter() - wall0
+    ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = float(np.sum(ms))
+    # the dominant kernel (K1 g2g_moments) alone, CUDA events on its launch stream, L2 flushed
+    k1_ms = []
+    for k in range(args.steps):
+        flush_buf.fill_(k & 0xFF)
+        a, b = k1_events[k]
+        eng.time_moments(a, b)
+    torch.cuda.synchronize()
+    k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    clocks = sampler.finish() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * G / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: public API, pinned host inputs -> host results --------------------------------
+    Xr_pin = torch.from_numpy(Xr).pin_memory()
+    Xq_pin = torch.from_numpy(Xq).pin_memory()
+    e2e_ms = []
+    d2h = 0
+    for k in range(args.e2e_steps + 1):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        aligner = Main.RefQueryAligner(AnnDataLite(Xr_pin, tr, genes), AnnDataLite(Xq_pin, tq, genes), genes, T,
+                                       verbose=False)
+        aligner.align_all_pairs()
+        n_match = sum(a.alignment_str.count("M") for a in aligner.results)  # touch every result
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if k > 0:  # first call is warm-up
+            e2e_ms.append(dt * 1e3)
+        d2h = int(sum(v.nbytes for v in aligner._host.values()))
+        del aligner
+    e2e_t = float(np.mean(e2e_ms)) * 1e-3
+    if world > 1:
+        t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_t = float(t.item())
+    h2d = int(Xr.nbytes + Xq.nbytes + tr.nbytes + tq.nbytes)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        nr, nq = Xr.shape[0], Xq.shape[0]
+        alg_bytes = 4.0 * (nr + nq) * G + 8.0 * (nr + nq)
+        k1 = float(np.mean(k1_ms)) * 1e-3
+        achieved = alg_bytes / k1 / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 products / f64 accumulation (interpolation), f64 (cost + DP)",
+            "data": "synthetic",
+            "config": config_dict(args.workload, args.dropout, world,
+                                  {"cuda_graph": graph is not None, "wall_s_timed_region": wall}),
+            "e2e": {"value": world * G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_t * 1e3, "steps": len(e2e_ms),
+                    "what": "Main.RefQueryAligner(...) + align_all_pairs() from pinned host arrays to host result objects"},
+            "gpu_launches": eng.launches_per_run * args.steps,
+            "roofline": {"kernel": "moments_kernel (K1 g2g_moments)", "bound": "hbm", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / (float(np.mean(ms)))},
+            "clocks": clocks,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            t0 = time.perf_counter()
+            rate = cpu_port_rate(Xr, tr, Xq, tq, T, args.cpu_genes, 1)
+            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+                                    "sample": "%d genes of the workload at full cell counts, oracle port "
+                                              "(oracle/g2g_oracle.py align_gene_faithful), %.1f s"
+                                              % (min(args.cpu_genes, G), time.perf_counter() - t0)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

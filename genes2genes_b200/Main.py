@@ -1,0 +1,535 @@
+"""Drop-in for the per-gene alignment path of ``genes2genes.Main`` (reference v0.2.0):
+
+    aligner = Main.RefQueryAligner(adata_ref, adata_query, gene_list, n_interpolation_points)
+    aligner.align_all_pairs()
+    aligner.results            # list of AligmentObj, gene_list order
+    aligner.results_map[gene]  # dict gene -> AligmentObj
+
+All genes are interpolated and aligned in one batch by ``libg2g.so`` on a B200; the objects here
+are thin views over the batched result arrays, with the reference's attribute names
+(SURVEY.md section 8(b)).  Heavy per-gene attributes (dense DP matrices, DE statistics) are
+produced on first access.
+"""
+import re
+
+import numpy as np
+
+from . import OrgAlign as orgalign
+from . import TimeSeriesPreprocessor
+from . import _lib
+from . import engine as _engine
+
+__version__ = "v0.2.0-b200"
+
+_FLAG_BAD_SIGMA = 0x10
+
+
+class hcolors:
+    MATCH = "\033[92m"
+    INSERT = "\033[91m"
+    DELETE = "\033[91m"
+    STOP = "\033[0m"
+
+
+# ---------------------------------------------------------------------------------------------------
+# alignment-string post-processing (reference: DEAnalyser, Main.py:568-835)
+# ---------------------------------------------------------------------------------------------------
+def _index_digits(marks):
+    """Index line under an alignment row: '*' consumes the next index (digits cycle 0..9),
+    '^' repeats the previous one, '-' leaves a blank; every other character (the ANSI colour
+    codes embedded in the row) is skipped (Main.py:579-595)."""
+    out = []
+    i = 0
+    for ch in marks:
+        if ch == "-":
+            out.append(" ")
+        elif ch == "^":
+            out.append(str(i - 1))
+        elif ch == "*":
+            if i >= 10:
+                i = 0
+            out.append(str(i))
+            i += 1
+    return "".join(out)
+
+
+def alignment_visual(s):
+    """(al_visual, colored_alignment_str, regions) of a five-state string (Main.py:602-712).
+
+    ``regions`` = (S_match, T_match, S_non_match, T_non_match, abstract_regions) from the
+    five-state walk over maximal runs."""
+    ref_row, qry_row, colored = [], [], []
+    S_match, T_match, S_non, T_non, abstract = [], [], [], [], []
+    i = j = 0
+    for m in re.finditer(r"M+|W+|V+|D+|I+", s):
+        ch, n = m.group(0)[0], len(m.group(0))
+        if ch == "M":
+            S_match.append([j, j + n - 1])
+            T_match.append([i, i + n - 1])
+            i += n
+            j += n
+            ref_row.append(hcolors.MATCH + "*" * n + hcolors.STOP)
+            qry_row.append(hcolors.MATCH + "*" * n + hcolors.STOP)
+            abstract.append("M")
+        elif ch == "V":
+            T_match.append([i, i + n - 1])
+            i += n
+            ref_row.append("^" * n)
+            qry_row.append(hcolors.MATCH + "*" * n + hcolors.STOP)
+            abstract.append("V")
+        elif ch == "W":
+            S_match.append([j, j + n - 1])
+            j += n
+            ref_row.append(hcolors.MATCH + "*" * n + hcolors.STOP)
+            qry_row.append("^" * n)
+            abstract.append("W")
+        elif ch == "I":
+            T_non.append([i, i + n - 1])
+            i += n
+            ref_row.append("-" * n)
+            qry_row.append(hcolors.INSERT + "*" * n + hcolors.STOP)
+        else:  # D
+            S_non.append([j, j + n - 1])
+            j += n
+            ref_row.append(hcolors.DELETE + "*" * n + hcolors.STOP)
+            qry_row.append("-" * n)
+        colour = hcolors.MATCH if ch in "MWV" else hcolors.INSERT
+        colored.append(colour + ch * n + hcolors.STOP)
+    a1, a2 = "".join(ref_row), "".join(qry_row)
+    index_line = "".join(str(k % 10) for k in range(len(s)))
+    visual = (index_line + " Alignment index \n" + _index_digits(a1) + " Reference index" + "\n" + a1 + "\n" + a2
+              + "\n" + _index_digits(a2) + " Query index" + "\n" + s + " 5-state string ")
+    return visual, "".join(colored), (S_match, T_match, S_non, T_non, abstract)
+
+
+def matched_time_points(s):
+    """Pairs of (reference bin, query bin) matched through M, W or V (Main.py:716-773).
+
+    The reference keeps two cursors that lag behind by one on the side a warp repeats; the
+    bookkeeping below restates its transitions: ``i`` / ``j`` are the next unconsumed query /
+    reference bins, and entering or leaving a warp run adjusts the repeated side."""
+    i = j = 0
+    S_pts, T_pts = [], []
+    prev = ""
+    for ch in s:
+        if ch in "MID":
+            # leaving a warp run: the side the warp was repeating has to move on
+            if prev == "W":
+                i += 1
+            elif prev == "V":
+                j += 1
+        if ch == "M":
+            T_pts.append(i)
+            S_pts.append(j)
+            i += 1
+            j += 1
+        elif ch == "W":  # reference advances, query bin repeats
+            if prev == "V":
+                i -= 1
+                j += 1
+            elif prev != "W":
+                i -= 1
+            T_pts.append(i)
+            S_pts.append(j)
+            j += 1
+        elif ch == "V":  # query advances, reference bin repeats
+            if prev == "W":
+                j -= 1
+                i += 1
+            elif prev != "V":
+                j -= 1
+            T_pts.append(i)
+            S_pts.append(j)
+            i += 1
+        elif ch == "I":
+            i += 1
+        elif ch == "D":
+            j += 1
+        prev = ch
+    return np.array(S_pts), np.array(T_pts)
+
+
+class AligmentObj:
+    """Alignment result of one gene (reference: Main.py:33-177; the class name keeps the
+    reference's spelling).  A view over the aligner's batched arrays."""
+
+    def __init__(self, aligner, gene_idx, gene, S, T, fwd_DP, landscape_obj):
+        self._aligner = aligner
+        self._gene_idx = gene_idx
+        self.gene = gene
+        self.S = S
+        self.T = T
+        self.alignment_str = fwd_DP.alignment_str
+        self.landscape_obj = landscape_obj
+        self.fwd_DP = fwd_DP
+        self.bwd_DP = None
+        regions = fwd_DP.get_matched_regions()
+        self.match_regions_S, self.match_regions_T, self.non_match_regions_S, self.non_match_regions_T = regions
+        self.compute_series_match_percentage()
+        self._visual = None
+        self._points = None
+        self._de = None
+
+    # -- percentages (Main.py:103-127) ------------------------------------------------------------
+    def compute_series_match_percentage(self):
+        s = self.alignment_str
+        n_m, n_v, n_w = s.count("M"), s.count("V"), s.count("W")
+        self.match_percentage = round(((n_m + n_v + n_w) / len(s)) * 100, 2)
+        self.match_percentage_T = round(((n_m + n_v) / len(self.T.mean_trend)) * 100, 2)
+        self.match_percentage_S = round(((n_m + n_w) / len(self.S.mean_trend)) * 100, 2)
+
+    def get_series_match_percentage(self):
+        return self.match_percentage, self.match_percentage_S, self.match_percentage_T
+
+    def get_opt_alignment_cost(self):
+        return self.fwd_DP.opt_cost
+
+    # -- lazily derived fields (reference computes them eagerly in run_DEAnalyser, Main.py:129-138) --
+    def _ensure_visual(self):
+        if self._visual is None:
+            self._visual = alignment_visual(self.alignment_str)
+        return self._visual
+
+    @property
+    def al_visual(self):
+        return self._ensure_visual()[0]
+
+    @property
+    def colored_alignment_str(self):
+        return self._ensure_visual()[1]
+
+    def _ensure_points(self):
+        if self._points is None:
+            self._points = matched_time_points(self.alignment_str)
+        return self._points
+
+    @property
+    def match_points_S(self):
+        return self._ensure_points()[0]
+
+    @property
+    def match_points_T(self):
+        return self._ensure_points()[1]
+
+    @property
+    def l2fold_changes(self):
+        """[log2(mean(S bin)/mean(T bin)), S bin, T bin] per matched pair (Main.py:777-783)."""
+        s, t = self._ensure_points()
+        with np.errstate(all="ignore"):
+            return [[np.log2(np.mean(self.S.data_bins[a]) / np.mean(self.T.data_bins[b])), a, b]
+                    for a, b in zip(s, t)]
+
+    @property
+    def matched_region_DE_info(self):
+        """Per matched bin pair: Wilcoxon / KS / t-test p-values and the compression statistic
+        (Main.py:791-835).  Computed with scipy on first access (the reference pays this for every
+        gene inside ``align_all_pairs``)."""
+        if self._de is None:
+            self._de = _de_info(self)
+        return self._de
+
+    # -- printing -----------------------------------------------------------------------------------
+    def print(self):
+        print("Fwd opt cost", self.fwd_DP.opt_cost)
+        print("5-state alignment string: ", self.fwd_DP.alignment_str)
+        print("Ref matched time points ranges: ", self.match_regions_S)
+        print("Query matched time points ranges: ", self.match_regions_T)
+        print("Ref mismatched time points ranges: ", self.non_match_regions_S)
+        print("Query mismatched time points ranges: ", self.non_match_regions_T)
+
+    def print_alignment(self):
+        print(self.al_visual)
+        print("Matched percentages: ")
+        p1, p2, p3 = self.get_series_match_percentage()
+        print("w.r.t alignment: ", p1, "%")
+        print("w.r.t ref: ", p2, "%")
+        print("w.r.t query: ", p3, "%")
+
+    def plot_mean_trends(self):
+        self.S.plot_mean_trend(color="forestgreen")
+        self.T.plot_mean_trend(color="midnightblue")
+
+
+def _de_info(a):
+    import pandas as pd
+    import scipy.stats as stats
+
+    s, t = a.match_points_S, a.match_points_T
+    S_bins, T_bins = a.S.data_bins, a.T.data_bins
+    cost = _engine_cost_matrix(a)
+    rows = []
+    with np.errstate(all="ignore"):
+        for k in range(len(s)):
+            l2fc = np.log2(np.mean(S_bins[s[k]]) / np.mean(T_bins[t[k]]))
+            # the reference tests the *reference-side* bins s[k] and t[k] for equality (Main.py:811-814)
+            if not np.any(np.asarray(S_bins[s[k]]) - np.asarray(S_bins[t[k]])):
+                pw = pk = pt = 0.0
+            else:
+                pw = np.round(stats.wilcoxon(S_bins[s[k]], T_bins[t[k]])[1], 6)
+                pk = np.round(stats.ks_2samp(S_bins[s[k]], T_bins[t[k]])[1], 6)
+                pt = np.round(stats.ttest_ind(S_bins[s[k]], T_bins[t[k]])[1], 6)
+            rows.append([s[k], t[k], a.S.time_points[s[k]], a.T.time_points[t[k]],
+                         np.round(cost[t[k], s[k]], 7), l2fc, pw, pk, pt])
+    df = pd.DataFrame(rows, columns=["ref_bin", "query_bin", "ref_pseudotime", "query_pseudotime", "Delta",
+                                     "l2fc", "wilcox", "ks2", "ttest"])
+    return df
+
+
+def _engine_cost_matrix(a):
+    """Closed form of the MML match cost (device formula, csrc/g2g_dp.cu) for one gene on the host."""
+    n = _engine.N_SAMPLES
+    mS, sS = a.S.mean_trend[None, :], a.S.std_trend[None, :]
+    mT, sT = a.T.mean_trend[:, None], a.T.std_trend[:, None]
+    d2 = (mT - mS) ** 2
+    term = (sT ** 2 + d2) / sS ** 2 + (sS ** 2 + d2) / sT ** 2 - 2.0
+    return (n / 2.0 * term - 2.0 * _engine.model_constant(n) + np.log(sS) + np.log(sT)) / (4.0 * n)
+
+
+# ---------------------------------------------------------------------------------------------------
+class _LazyPairs(dict):
+    """``aligner.pairs``: gene -> [S, T] interpolated series, filled on demand from the batch
+    (the reference memoises ``run_interpolation`` per gene here, Main.py:417-418)."""
+
+    def __init__(self, aligner):
+        super().__init__()
+        self._aligner = aligner
+
+    def __missing__(self, gene):
+        idx = self._aligner._gene_index[gene]
+        st = self._aligner._series_pair(idx)
+        self[gene] = st
+        return st
+
+
+class RefQueryAligner:
+    """Entry point of the alignment (reference: Main.py:180-564).
+
+    ``RefQueryAligner(adata_ref, adata_query, gene_list, n_interpolation_points[, adaptive_kernel])``.
+    ``adata_*`` need ``.X`` (dense array, torch tensor or scipy sparse; cells x genes),
+    ``.obs['time']`` in [0, 1], ``.var_names`` and ``.obs_names``.
+    """
+
+    def __init__(self, *args, device=None, verbose=True):
+        self._verbose = verbose
+        self._say("===============================================================================================================")
+        self._say("Genes2Genes (" + __version__ + ")")
+        self._say("Dynamic programming alignment of gene pseudotime trajectories using a bayesian information-theoretic framework")
+        self._say("===============================================================================================================")
+        if len(args) == 4:
+            adaptive_kernel = False
+        elif len(args) == 5:
+            self._say("Running in adaptive interpolation mode")
+            adaptive_kernel = args[4]
+        else:
+            raise TypeError("RefQueryAligner expects (adata_ref, adata_query, gene_list, n_interpolation_points"
+                            "[, adaptive_kernel])")
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("genes2genes_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        _lib.load()
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        adata_ref, adata_query, gene_list, n_bins = args[0], args[1], args[2], args[3]
+        self.adata_ref_full, self.adata_query_full = adata_ref, adata_query
+        self.gene_list = gene_list
+        self.n_artificial_time_points = int(n_bins)
+        self.ref_time = np.asarray(adata_ref.obs["time"], dtype=np.float64)
+        self.query_time = np.asarray(adata_query.obs["time"], dtype=np.float64)
+        self._gene_index = {g: k for k, g in enumerate(gene_list)}
+        self.pairs = _LazyPairs(self)
+        self.state_params = [0.99, 0.1, 0.7]  # same defaults as the reference (Main.py:218)
+        self.no_extreme_cases = False
+
+        k = 1
+        self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
+            self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
+            obs_names=getattr(adata_ref, "obs_names", None)).run()
+        self.TrajInt_Q = TimeSeriesPreprocessor.TrajectoryInterpolator(
+            self.query_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
+            obs_names=getattr(adata_query, "obs_names", None)).run()
+        with torch.cuda.device(self.device):
+            Xr = self._pack(adata_ref, self.TrajInt_R.order)
+            Xq = self._pack(adata_query, self.TrajInt_Q.order)
+            self._engine = _engine.AlignmentEngine(
+                Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(gene_list),
+                self.n_artificial_time_points, self.TrajInt_R.kernel_denominators(),
+                self.TrajInt_Q.kernel_denominators(), self.state_params, self.device)
+        self._say("Interpolator initialization completed")
+        self._interp = None
+        self._host = None
+        self._say("Aligner initialised to align trajectories of", adata_ref.shape[0], "reference cells &",
+                  adata_query.shape[0], "query cells in terms of", len(self.gene_list), "genes")
+
+    def _say(self, *a):
+        if self._verbose:
+            print(*a)
+
+    # -- input packing ------------------------------------------------------------------------------
+    def _pack(self, adata, order):
+        """``adata[order][:, gene_list].X`` as a packed f32 device matrix."""
+        var_names = [str(v) for v in adata.var_names]
+        if list(self.gene_list) == var_names:
+            gene_idx = None
+        else:
+            pos = {g: k for k, g in enumerate(var_names)}
+            gene_idx = np.asarray([pos[g] for g in self.gene_list], dtype=np.int32)
+        X = adata.X
+        identity = bool(np.all(order[1:] > order[:-1])) if len(order) > 1 else True
+        row_order = None if identity else order
+        try:
+            import scipy.sparse as sp
+            is_sparse = sp.issparse(X)
+        except Exception:  # scipy always ships with the reference's dependencies; be permissive
+            is_sparse = False
+        if is_sparse:
+            return _engine.pack_csr(X.tocsr(), row_order, gene_idx, X.shape[1], self.device)
+        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
+            X = X.todense()
+        if isinstance(X, np.matrix):
+            X = np.asarray(X)
+        return _engine.pack_dense(X, row_order, gene_idx, self.device)
+
+    @property
+    def ref_mat(self):
+        return self._dense_frame(self.adata_ref_full)
+
+    @property
+    def query_mat(self):
+        return self._dense_frame(self.adata_query_full)
+
+    @staticmethod
+    def _dense_frame(adata):
+        """cells x genes DataFrame of the *un-subset* matrix, as the reference keeps (Main.py:229-247)."""
+        import pandas as pd
+        X = adata.X
+        X = X.todense() if hasattr(X, "todense") else X
+        if hasattr(X, "cpu"):
+            X = X.cpu().numpy()
+        return pd.DataFrame(np.asarray(X), columns=adata.var_names, index=adata.obs_names)
+
+    # -- stages ---------------------------------------------------------------------------------------
+    def _run_batch(self):
+        import torch
+        eng = self._engine
+        with torch.cuda.device(self.device):
+            eng.set_state_params(self.state_params)
+            if self._interp is None:
+                eng.run_interpolation()
+                self._interp = True
+            eng.run_dp()
+            self._host = eng.results_to_host()
+        bad = np.nonzero(self._host["flags"] & _FLAG_BAD_SIGMA)[0]
+        if len(bad):
+            g = self.gene_list[int(bad[0])]
+            raise ValueError("Expected parameter scale of the interpolated distribution to be positive "
+                             "(GreaterThan(lower_bound=0.0)); gene %r has a zero or invalid interpolated "
+                             "standard deviation (%d gene(s) affected)" % (g, len(bad)))
+        return self._host
+
+    def _series_pair(self, idx):
+        if self._host is None:
+            self._run_batch()
+        h, eng = self._host, self._engine
+        ms, tr = h["musigma"][idx], h["trends"][idx]
+        gene = self.gene_list[idx]
+        S = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[0], ms[1], tr[0], tr[1],
+                                                     self.TrajInt_R.interpolation_points, eng.eps)
+        T = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[2], ms[3], tr[2], tr[3],
+                                                     self.TrajInt_Q.interpolation_points, eng.eps)
+        return [S, T]
+
+    def _make_result(self, idx, host=None):
+        h = self._host if host is None else host
+        gene = self.gene_list[idx]
+        S, T = self.pairs[gene]
+        n = int(h["align_len"][idx])
+        s = h["align_str"][idx, :n].tobytes().decode("ascii")
+        nT = self.n_artificial_time_points
+        dp = orgalign.DP5(self, idx, S, T, s, np.float64(h["opt_cost"][idx]), self.state_params)
+        land = orgalign.AlignmentLandscape(dp, h["l_states"][idx].reshape(nT + 1, nT + 1), nT, nT)
+        return AligmentObj(self, idx, gene, S, T, dp, land)
+
+    def _dense_dump(self, idx):
+        """Dense DP matrices / back-pointers / cost terms of one gene (K4 in dump mode)."""
+        import torch
+        eng = self._engine
+        if self._host is None:
+            self._run_batch()
+        with torch.cuda.device(self.device):
+            eng.set_state_params(self.state_params)
+            out = eng.run_dp(dump=True, gene_slice=slice(idx, idx + 1))
+            torch.cuda.current_stream().synchronize()
+        d = {k: out[k][0].cpu().numpy() for k in ("cost", "mats", "bp", "L")}
+        # null / match_len terms of OrgAlign.py:486-494 in closed form
+        tr = self._host["trends"][idx]
+        n = _engine.N_SAMPLES
+        K = n / 2.0 * np.log(2 * np.pi) + 1.0 - n * np.log(0.001)
+        C = _engine.model_constant(n)
+        mS, sS, mT, sT = tr[0][None, :], tr[1][None, :], tr[2][:, None], tr[3][:, None]
+        d2 = (mT - mS) ** 2
+        I_RS = K + n * np.log(sS) + n / 2.0
+        I_QT = K + n * np.log(sT) + n / 2.0
+        I_QS = K + n * np.log(sS) + n * (sT ** 2 + d2) / (2 * sS ** 2)
+        I_RT = K + n * np.log(sT) + n * (sS ** 2 + d2) / (2 * sT ** 2)
+        mod_S, mod_T = C - np.log(sS), C - np.log(sT)
+        null = (mod_S + I_RS + mod_T + I_QT) / (2 * n) + 0 * d2
+        match = 0.5 * ((mod_S + I_QS + I_RS) + (mod_T + I_RT + I_QT)) / (2 * n)
+        d["util"] = np.stack([null, match, d["cost"]])
+        return d
+
+    def run_interpolation(self, gene_idx):
+        """[S, T] interpolated series of one gene (reference: Main.py:307-410)."""
+        return self.pairs[self.gene_list[gene_idx]]
+
+    def align_single_pair(self, gene_idx):
+        """Align one gene with the current ``state_params`` (reference: Main.py:413-432)."""
+        import torch
+        if self._host is None:
+            self._run_batch()
+        eng = self._engine
+        with torch.cuda.device(self.device):
+            eng.set_state_params(self.state_params)
+            out = eng.run_dp(gene_slice=slice(gene_idx, gene_idx + 1))
+            torch.cuda.current_stream().synchronize()
+        one = {k: out[k].cpu().numpy() for k in ("align_str", "align_len", "opt_cost", "l_states")}
+        view = {k: _Shift(one[k], gene_idx) for k in one}
+        return self._make_result(gene_idx, view)
+
+    def align_all_pairs(self, concurrent=False, n_processes=None):
+        """Align every gene of ``gene_list`` (reference: Main.py:434-457).  ``concurrent`` /
+        ``n_processes`` are accepted for signature compatibility; the batch already runs all genes
+        concurrently on the GPU."""
+        self._say("Running gene-level alignment: \U0001F9EC")
+        self._run_batch()
+        self.results = [self._make_result(k) for k in range(len(self.gene_list))]
+        self.results_map = {a.gene: a for a in self.results}
+        self._say("Alignment completed! ✅")
+
+    # -- summaries ------------------------------------------------------------------------------------
+    def get_match_stat_for_all_genes(self):
+        import pandas as pd
+        rows = [a.get_series_match_percentage() for a in self.results]
+        df = pd.DataFrame(rows, columns=["match %", "match % S", "match % T"])
+        df["cluster_id"] = getattr(self, "cluster_ids", [None] * len(rows))
+        return df
+
+    def get_stat_table(self):
+        """Gene / alignment similarity / optimal cost table (the numeric part of the reference's
+        ``get_stat_df``, Main.py:459-477, without the plots)."""
+        import pandas as pd
+        return pd.DataFrame({
+            "Gene": list(self.gene_list),
+            "alignment_similarity_percentage": [a.match_percentage / 100 for a in self.results],
+            "opt_alignment_cost": [a.fwd_DP.opt_cost for a in self.results],
+        })
+
+
+class _Shift:
+    """Index adaptor so a one-gene result array can be addressed with the gene's global index."""
+
+    def __init__(self, arr, idx):
+        self._arr, self._idx = arr, idx
+
+    def __getitem__(self, key):
+        if isinstance(key, tuple):
+            return self._arr[(key[0] - self._idx,) + key[1:]]
+        return self._arr[key - self._idx]

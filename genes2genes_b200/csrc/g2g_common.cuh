@@ -1,0 +1,41 @@
+// Shared helpers for the libg2g kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "g2g.h"
+
+void g2g_set_error(const char* fmt, ...);
+
+#define G2G_CUDA_TRY(expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) {                                                            \
+      g2g_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return G2G_ERR_CUDA;                                                              \
+    }                                                                                   \
+  } while (0)
+
+#define G2G_REQUIRE(cond, msg)                                   \
+  do {                                                           \
+    if (!(cond)) {                                               \
+      g2g_set_error("%s: %s", __func__, msg);                    \
+      return G2G_ERR_ARG;                                        \
+    }                                                            \
+  } while (0)
+
+static inline int64_t g2g_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+static inline int64_t g2g_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
+
+// Bin tiling shared by K0 (table layout) and K1 (register tile): see g2g_layout_t.
+struct G2GTiling {
+  int n_groups, bins_per_group, row_floats, genes_per_thread;
+};
+static inline G2GTiling g2g_tiling(int n_bins) {
+  G2GTiling t;
+  t.n_groups = (int)g2g_ceil_div(n_bins, 56);
+  t.bins_per_group = (int)g2g_ceil_div(n_bins, t.n_groups);
+  t.row_floats = (int)g2g_round_up(t.bins_per_group + 2, 4);
+  t.genes_per_thread = t.bins_per_group <= 28 ? 2 : 1;
+  return t;
+}

@@ -1,0 +1,329 @@
+// K4  g2g_cost_dp: MML match cost + five-state (M,W,V,D,I) DP + traceback + landscape.
+//
+// One warp per gene.  Lane l owns the B = ceil((T+1)/32) DP columns [l*B, l*B+B); at step s it
+// fills row i = s - l + 1 of its columns (a skewed wavefront: lane l-1 finished row i one step
+// earlier), receiving the five values of its left neighbour's last column by warp shuffle.
+// All DP arithmetic is float64 adds/compares in the reference's order
+// ((prev + cost) + transition, first minimum wins; OrgAlign.py:344-450), so given equal costs the
+// five matrices, back-pointers, string and landscape are bit-identical to the reference.
+#include "g2g_common.cuh"
+#include <math.h>
+
+namespace {
+
+struct DpParams {
+  const double* trends;   // [G][4][T]
+  const double* cost_in;  // optional [G][T][T]
+  uint8_t* align_str;     // [G][2T]
+  int32_t* align_len;     // [G]
+  double* opt_cost;       // [G]
+  uint8_t* l_states;      // [G][(T+1)^2]
+  double* cost_out;       // optional
+  double* mats_out;       // optional [G][5][(T+1)^2]
+  int8_t* bp_out;         // optional
+  double* l_out;          // optional
+  long long n_genes;
+  int n_bins;
+  double trans[25];       // I[to][from]
+  double start[3];
+  double half_n;          // N/2
+  double inv_4n;          // 1/(4N)
+  double two_c;           // 2*C_model
+};
+
+constexpr int kWarpsPerBlock = 4;
+
+__host__ __device__ inline size_t dp_smem_per_warp(int T) {
+  size_t b = 0;
+  b += (size_t)4 * T * sizeof(double);                    // query-side per-bin terms
+  b += (size_t)T * T * sizeof(uint16_t);                  // packed back-pointers (5 x 3 bits)
+  b += (size_t)(T + 1) * (T + 1);                         // L states
+  b += (size_t)2 * T;                                     // reversed alignment string
+  return (b + 15) & ~(size_t)15;
+}
+
+struct Five {
+  double v[5];
+};
+
+__device__ __forceinline__ Five shfl_up5(const Five& a) {
+  Five r;
+#pragma unroll
+  for (int k = 0; k < 5; ++k) r.v[k] = __shfl_up_sync(0xffffffffu, a.v[k], 1);
+  return r;
+}
+
+// first minimum of (src[k] + c) + tr[k], k = 0..4  (list.index(min(list)), OrgAlign.py:428-437)
+__device__ __forceinline__ void best5(const Five& src, double c, const double* tr, double& best, int& arg) {
+  best = (src.v[0] + c) + tr[0];
+  arg = 0;
+#pragma unroll
+  for (int k = 1; k < 5; ++k) {
+    double cand = (src.v[k] + c) + tr[k];
+    if (cand < best) { best = cand; arg = k; }
+  }
+}
+__device__ __forceinline__ void best5_gap(const Five& src, const double* tr, double& best, int& arg) {
+  // gap cells cost 0.0 (OrgAlign.py:473-474, 499-500); (x + 0.0) + t == x + t bit for bit
+  best = src.v[0] + tr[0];
+  arg = 0;
+#pragma unroll
+  for (int k = 1; k < 5; ++k) {
+    double cand = src.v[k] + tr[k];
+    if (cand < best) { best = cand; arg = k; }
+  }
+}
+
+template <int B>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_constant__ DpParams p) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int T = p.n_bins;
+  const int nC = T + 1;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const long long g = (long long)blockIdx.x * kWarpsPerBlock + warp;
+  if (g >= p.n_genes) return;  // whole warp exits together; no block-level barriers below
+
+  unsigned char* base = smem_raw + (size_t)warp * dp_smem_per_warp(T);
+  double* q_mu = reinterpret_cast<double*>(base);
+  double* q_var = q_mu + T;
+  double* q_ivar = q_var + T;
+  double* q_ln = q_ivar + T;
+  uint16_t* bp = reinterpret_cast<uint16_t*>(q_ln + T);
+  uint8_t* ls = reinterpret_cast<uint8_t*>(bp + (size_t)T * T);
+  uint8_t* sbuf = ls + (size_t)nC * nC;
+
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+  const double* tr = p.trends + (size_t)g * 4 * T;
+  const bool have_cost = p.cost_in != nullptr;
+  const double* cin = have_cost ? p.cost_in + (size_t)g * T * T : nullptr;
+  double* cout = p.cost_out ? p.cost_out + (size_t)g * T * T : nullptr;
+  double* mout = p.mats_out ? p.mats_out + (size_t)g * 5 * nC * nC : nullptr;
+  int8_t* bout = p.bp_out ? p.bp_out + (size_t)g * 5 * nC * nC : nullptr;
+  double* lout = p.l_out ? p.l_out + (size_t)g * nC * nC : nullptr;
+
+  // ---- prologue: per-bin terms of the closed-form cost -----------------------------------
+  for (int t = lane; t < T; t += 32) {
+    double mu = tr[2 * T + t], sd = tr[3 * T + t];
+    q_mu[t] = mu;
+    q_var[t] = sd * sd;
+    q_ivar[t] = 1.0 / (sd * sd);
+    q_ln[t] = log(sd);
+  }
+  double s_mu[B], s_var[B], s_ivar[B], s_ln[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    int j = lane * B + b;
+    bool ok = (j >= 1 && j <= T);
+    double mu = ok ? tr[j - 1] : 0.0, sd = ok ? tr[T + j - 1] : 1.0;
+    s_mu[b] = mu;
+    s_var[b] = sd * sd;
+    s_ivar[b] = 1.0 / (sd * sd);
+    s_ln[b] = log(sd);
+  }
+
+  // ---- row 0 / column 0 initial values (OrgAlign.py:272-331) --------------------------------
+  // D[0][j] = (D[0][j-1] + 0.0) + (j==1 ? -ln ProbD : I_dd), sequentially from D[0][0] = 0
+  Five up[B];
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    int j = lane * B + b;
+    if (j == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) up[b].v[k] = 0.0;
+    } else {
+      double d = 0.0;
+      for (int jj = 1; jj <= j && jj <= T; ++jj) d = d + (jj == 1 ? p.start[1] : p.trans[3 * 5 + 3]);
+      up[b].v[0] = inf; up[b].v[1] = inf; up[b].v[2] = inf; up[b].v[3] = d; up[b].v[4] = inf;
+    }
+  }
+  // value of row 0 at the column left of this lane's first column (the first "diagonal" input)
+  Five nbr_prev;
+  {
+    int j = lane * B - 1;
+    if (j <= 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) nbr_prev.v[k] = 0.0;
+    } else {
+      double d = 0.0;
+      for (int jj = 1; jj <= j; ++jj) d = d + (jj == 1 ? p.start[1] : p.trans[3 * 5 + 3]);
+      nbr_prev.v[0] = inf; nbr_prev.v[1] = inf; nbr_prev.v[2] = inf; nbr_prev.v[3] = d; nbr_prev.v[4] = inf;
+    }
+  }
+  // row 0 of the landscape / dumps
+#pragma unroll
+  for (int b = 0; b < B; ++b) {
+    int j = lane * B + b;
+    if (j <= T) {
+      ls[j] = (j == 0) ? 0 : 3;
+      if (mout) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) mout[(size_t)k * nC * nC + j] = up[b].v[k];
+      }
+      if (bout) {
+#pragma unroll
+        for (int k = 0; k < 5; ++k) bout[(size_t)k * nC * nC + j] = (k == 3 && j >= 1) ? 3 : -1;
+      }
+      if (lout) lout[j] = (j == 0) ? 0.0 : up[b].v[3];
+    }
+  }
+  __syncwarp();
+
+  const int n_lanes = (nC + B - 1) / B;  // lanes that own at least one column
+  const int n_steps = T + n_lanes - 1;
+  for (int s = 0; s < n_steps; ++s) {
+    Five nbr = shfl_up5(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
+    const int i = s - lane + 1;
+    if (i >= 1 && i <= T && lane < n_lanes) {
+      const double t_mu = q_mu[i - 1], t_var = q_var[i - 1], t_ivar = q_ivar[i - 1], t_ln = q_ln[i - 1];
+      Five left = nbr, diag = nbr_prev;
+#pragma unroll
+      for (int b = 0; b < B; ++b) {
+        const int j = lane * B + b;
+        if (j > T) break;
+        Five cur;
+        int lstate;
+        if (j == 0) {
+          // column 0: only I is finite (OrgAlign.py:287-318)
+          cur.v[0] = inf; cur.v[1] = inf; cur.v[2] = inf; cur.v[3] = inf;
+          cur.v[4] = up[b].v[4] + (i == 1 ? p.start[0] : p.trans[4 * 5 + 4]);
+          lstate = 4;
+          if (bout) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) bout[(size_t)k * nC * nC + (size_t)i * nC] = (k == 4) ? 4 : -1;
+          }
+        } else {
+          double c;
+          if (have_cost) {
+            c = cin[(size_t)(i - 1) * T + (j - 1)];
+          } else {
+            double d = t_mu - s_mu[b];
+            double d2 = d * d;
+            double a = (t_var + d2) * s_ivar[b] + (s_var[b] + d2) * t_ivar - 2.0;
+            c = (p.half_n * a - p.two_c + s_ln[b] + t_ln) * p.inv_4n;
+          }
+          if (cout) cout[(size_t)(i - 1) * T + (j - 1)] = c;
+          int am, aw, av, ad, ai;
+          if (i == 1 && j == 1) {  // OrgAlign.py:344-350
+            cur.v[0] = (diag.v[0] + c) + p.start[2];
+            am = 0;
+          } else {
+            best5(diag, c, &p.trans[0], cur.v[0], am);
+          }
+          best5(left, c, &p.trans[5], cur.v[1], aw);
+          best5(up[b], c, &p.trans[10], cur.v[2], av);
+          best5_gap(left, &p.trans[15], cur.v[3], ad);
+          best5_gap(up[b], &p.trans[20], cur.v[4], ai);
+          bp[(size_t)(i - 1) * T + (j - 1)] = (uint16_t)(am | (aw << 3) | (av << 6) | (ad << 9) | (ai << 12));
+          double lbest = cur.v[0];
+          lstate = 0;
+#pragma unroll
+          for (int k = 1; k < 5; ++k)
+            if (cur.v[k] < lbest) { lbest = cur.v[k]; lstate = k; }
+          if (bout) {
+            size_t o = (size_t)i * nC + j;
+            bout[o] = am; bout[(size_t)nC * nC + o] = aw; bout[(size_t)2 * nC * nC + o] = av;
+            bout[(size_t)3 * nC * nC + o] = ad; bout[(size_t)4 * nC * nC + o] = ai;
+          }
+        }
+        ls[(size_t)i * nC + j] = (uint8_t)lstate;
+        if (mout) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k) mout[(size_t)k * nC * nC + (size_t)i * nC + j] = cur.v[k];
+        }
+        if (lout) lout[(size_t)i * nC + j] = cur.v[lstate];
+        diag = up[b];   // (i-1, j) is the diagonal input of column j+1
+        left = cur;     // (i, j) is its left input
+        up[b] = cur;
+      }
+      nbr_prev = nbr;
+    }
+  }
+  __syncwarp();
+
+  // ---- traceback (OrgAlign.py:539-607) by the lane that owns column T ------------------------
+  const int owner = T / B;
+  const int ob = T - owner * B;
+  int len = 0;
+  if (lane == owner) {
+    Five fin;
+#pragma unroll
+    for (int b = 0; b < B; ++b)
+      if (b == ob) fin = up[b];
+    double best = fin.v[0];
+    int state = 0;
+#pragma unroll
+    for (int k = 1; k < 5; ++k)
+      if (fin.v[k] < best) { best = fin.v[k]; state = k; }
+    p.opt_cost[g] = best;
+    int i = T, j = T;
+    const int cap = 2 * T;
+    while ((i > 0 || j > 0) && len < cap) {
+      int prev;
+      if (i == 0) prev = 3;        // row 0: D <- D   (backtrackers_D[0][j] = [0, j-1, 3])
+      else if (j == 0) prev = 4;   // column 0: I <- I
+      else prev = (bp[(size_t)(i - 1) * T + (j - 1)] >> (3 * state)) & 7;
+      if (i == 0) state = 3;
+      if (j == 0 && i > 0) state = 4;
+      sbuf[cap - 1 - len] = "MWVDI"[state];
+      ++len;
+      if (state == 0) { --i; --j; }
+      else if (state == 1 || state == 3) { --j; }
+      else { --i; }
+      state = prev;
+    }
+    p.align_len[g] = len;
+  }
+  len = __shfl_sync(0xffffffffu, len, owner);
+  __syncwarp();
+  uint8_t* so = p.align_str + (size_t)g * 2 * T;
+  for (int k = lane; k < 2 * T; k += 32) so[k] = (k < len) ? sbuf[2 * T - len + k] : 0;
+  uint8_t* lo = p.l_states + (size_t)g * nC * nC;
+  for (int k = lane; k < nC * nC; k += 32) lo[k] = ls[k];
+}
+
+template <int B>
+int launch_dp(const DpParams& p, cudaStream_t stream) {
+  size_t smem = dp_smem_per_warp(p.n_bins) * kWarpsPerBlock;
+  if (smem > 48 * 1024) {
+    G2G_CUDA_TRY(cudaFuncSetAttribute(dp_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  unsigned blocks = (unsigned)g2g_ceil_div(p.n_genes, kWarpsPerBlock);
+  dp_kernel<B><<<blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+  G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+
+}  // namespace
+
+extern "C" int g2g_cost_dp(const double* trends, int64_t n_genes, int32_t n_bins, const double* trans,
+                           const double* start, double c_model, int32_t n_samples, const double* cost_in,
+                           uint8_t* align_str, int32_t* align_len, double* opt_cost, uint8_t* l_states,
+                           double* cost_out, double* mats_out, int8_t* bp_out, double* l_out, void* stream) {
+  G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
+  G2G_REQUIRE(n_genes >= 0, "negative n_genes");
+  G2G_REQUIRE(trans && start, "trans/start are required host pointers");
+  G2G_REQUIRE(align_str && align_len && opt_cost && l_states, "null output pointer");
+  G2G_REQUIRE(trends || cost_in, "need trends or cost_in");
+  G2G_REQUIRE(trends != nullptr, "trends is required (its values are unused only when cost_in is given)");
+  if (n_genes == 0) return G2G_OK;
+  DpParams p;
+  p.trends = trends; p.cost_in = cost_in; p.align_str = align_str; p.align_len = align_len;
+  p.opt_cost = opt_cost; p.l_states = l_states; p.cost_out = cost_out; p.mats_out = mats_out;
+  p.bp_out = bp_out; p.l_out = l_out; p.n_genes = n_genes; p.n_bins = n_bins;
+  for (int k = 0; k < 25; ++k) p.trans[k] = trans[k];
+  for (int k = 0; k < 3; ++k) p.start[k] = start[k];
+  p.half_n = n_samples / 2.0;
+  p.inv_4n = 1.0 / (4.0 * n_samples);
+  p.two_c = 2.0 * c_model;
+  cudaStream_t st = (cudaStream_t)stream;
+  int nC = n_bins + 1;
+  int B = (nC + 31) / 32;
+  switch (B) {
+    case 1: return launch_dp<1>(p, st);
+    case 2: return launch_dp<2>(p, st);
+    case 3: return launch_dp<3>(p, st);
+    case 4: return launch_dp<4>(p, st);
+    default: return launch_dp<5>(p, st);
+  }
+}

@@ -1,0 +1,437 @@
+// K1  g2g_moments: single pass over the expression matrix (cells x genes, f32) of up to two
+// datasets, producing per (gene, bin) the shifted weighted moments
+//     A = sum_c w[t,c] (x_c - a),   B = sum_c w[t,c] (x_c - a)^2,   C = sum_c (x_c - a)
+// and the non-zero counts per pseudotime window.  Replaces the per-gene pandas/numpy loop of
+// TimeSeriesPreprocessor.compute_stat (TSP.py:161-174) and the counts of Main.py:298-301,344-363.
+//
+// Structure (B200): persistent CTAs walk a static list of work items (gene tile x cell range).
+// [64 cells x GT genes] tiles of X are streamed with TMA (cp.async.bulk.tensor.2d) and the matching
+// 64 rows of the weight table with a 1-D bulk copy into a ring of shared-memory stages guarded by
+// mbarriers; the warp that finishes a stage last re-arms it with the next tile, so there is no
+// producer warp and no blocking hand-off.  Eight warps each take 8 cells of a stage; every thread owns GX
+// genes x TB bins x {A,B} float accumulators in registers (an FFMA register tile: the weights are
+// warp-broadcast LDS.128, X is a conflict-free LDS).  Every kFlushStages stages the f32 partials
+// are added into CTA-wide f64 accumulators in shared memory, warp after warp in a fixed order, so
+// results do not depend on scheduling; the item's f64 sums go to its own slot of `part_f64`.
+#include "g2g_common.cuh"
+#include <cuda.h>
+
+namespace {
+
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = kConsumerWarps * 32;
+constexpr int kCellTile = G2G_CELL_TILE;              // rows per stage
+constexpr int kCellsPerWarp = kCellTile / kConsumerWarps;
+constexpr int kFlushStages = 8;                        // f32 run length per thread = 8 stages * 8 cells = 64 cells
+constexpr int kMaxSides = 2;
+
+struct MomSide {
+  const float* wtab;     // [n_groups][n_pad][RF]
+  const float* pilot;    // [G]
+  double* part_f64;      // [n_split][2T+1][g_stride]
+  int32_t* part_i32;     // [n_split][T][g_stride]
+  long long n_pad;
+  long long cells_per_item;
+  int n_split;
+  int item_base;         // first item index of this side
+};
+
+struct MomParams {
+  CUtensorMap tmap[kMaxSides];
+  MomSide side[kMaxSides];
+  long long n_genes, g_stride;
+  int n_sides, n_bins, n_groups, n_gtiles, n_items, n_stages;
+};
+
+// ---- raw PTX helpers (mbarrier + TMA) ----------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() { __syncthreads(); }
+
+template <int TB, int GX>
+struct Cfg {
+  static constexpr int GT = 32 * GX;                                  // genes per CTA tile
+  static constexpr int RF = (TB + 2 + 3) / 4 * 4;                     // floats per weight-table row
+  static constexpr int NQ = 2 * TB + 1;                               // f64 accumulator rows (A, B, C)
+  static constexpr int XBYTES = kCellTile * GT * 4;
+  static constexpr int WBYTES = kCellTile * RF * 4;
+  static constexpr int STAGE_BYTES = XBYTES + WBYTES;
+};
+
+struct Item {
+  int side, bg, split, gt, n_tiles;
+  long long row0;
+};
+
+__device__ __forceinline__ Item decode_item(const MomParams& p, int item) {
+  Item it;
+  it.side = (p.n_sides > 1 && item >= p.side[1].item_base) ? 1 : 0;
+  const MomSide& s = p.side[it.side];
+  int r = item - s.item_base;
+  it.gt = r % p.n_gtiles;
+  r /= p.n_gtiles;
+  it.split = r % s.n_split;
+  it.bg = r / s.n_split;
+  it.row0 = (long long)it.split * s.cells_per_item;
+  long long rows = s.n_pad - it.row0;
+  if (rows > s.cells_per_item) rows = s.cells_per_item;
+  it.n_tiles = (int)(rows / kCellTile);
+  return it;
+}
+
+#ifndef G2G_MOM_MIN_BLOCKS
+#define G2G_MOM_MIN_BLOCKS 1   // CTAs per SM the register budget is sized for (tuning knob)
+#endif
+template <int TB, int GX>
+__global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(const __grid_constant__ MomParams p) {
+  using C = Cfg<TB, GX>;
+  constexpr int kCellUnroll = (2 * TB * GX <= 64) ? 2 : 1;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int n_stages = p.n_stages;
+  // layout: [stages][X tile | W slice] | acc64 [NQ][GT] | cnt [n_bins][GT] | barriers
+  unsigned char* stage_base = smem;
+  double* acc64 = reinterpret_cast<double*>(smem + (size_t)n_stages * C::STAGE_BYTES);
+  int* cnt_s = reinterpret_cast<int*>(acc64 + C::NQ * C::GT);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(cnt_s + (size_t)p.n_bins * C::GT);
+  uint64_t* flush_bar = full_bar + n_stages;
+  int* done = reinterpret_cast<int*>(flush_bar + kConsumerWarps);  // warps finished with each stage
+  int* cursor = done + n_stages;                                    // {next item, next tile} to load
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done[s] = 0;
+    }
+    cursor[0] = blockIdx.x;
+    cursor[1] = 0;
+    for (int w = 0; w < kConsumerWarps; ++w) mbar_init(&flush_bar[w], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int k = threadIdx.x; k < C::NQ * C::GT; k += kThreads) acc64[k] = 0.0;
+  for (int k = threadIdx.x; k < p.n_bins * C::GT; k += kThreads) cnt_s[k] = 0;
+  __syncthreads();
+  if (threadIdx.x == 0) mbar_arrive(&flush_bar[0]);  // warp 0 may flush first
+
+  // Load the next tile of this CTA's item sequence into `slot`.  Only one thread runs this at a
+  // time: the prologue, then whichever warp finished the previous occupant of the slot last.
+  auto issue_next = [&](int slot_i) {
+    const int item = cursor[0];
+    if (item >= p.n_items) return;
+    const int tile = cursor[1];
+    const Item it = decode_item(p, item);
+    const MomSide& s = p.side[it.side];
+    const float* wsrc = s.wtab + ((size_t)it.bg * s.n_pad + (size_t)it.row0 + (size_t)tile * kCellTile) * C::RF;
+    unsigned char* dst = stage_base + (size_t)slot_i * C::STAGE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[slot_i], C::STAGE_BYTES);
+    tma_load_2d(dst, &p.tmap[it.side], it.gt * C::GT, (int)(it.row0 + (long long)tile * kCellTile),
+                &full_bar[slot_i]);
+    bulk_load_1d(dst + C::XBYTES, wsrc, C::WBYTES, &full_bar[slot_i]);
+    if (tile + 1 == it.n_tiles) { cursor[0] = item + gridDim.x; cursor[1] = 0; }
+    else cursor[1] = tile + 1;
+  };
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) issue_next(s);
+    __threadfence_block();
+  }
+  __syncthreads();
+
+  // ================= consumers ====================================================================
+  float accA[GX][TB], accB[GX][TB], accC[GX];
+  int cnt[GX];
+#pragma unroll
+  for (int x = 0; x < GX; ++x) {
+    accC[x] = 0.0f;
+    cnt[x] = 0;
+#pragma unroll
+    for (int t = 0; t < TB; ++t) { accA[x][t] = 0.0f; accB[x][t] = 0.0f; }
+  }
+  int slot = 0;
+  uint32_t phase = 0, flush_phase = 0;
+
+  // ordered f32 -> f64 flush: warp w adds after warp w-1 (token passed through flush_bar)
+  auto flush = [&]() {
+    mbar_wait(&flush_bar[warp], flush_phase);
+    flush_phase ^= 1;
+#pragma unroll
+    for (int t = 0; t < TB; ++t) {
+#pragma unroll
+      for (int x = 0; x < GX; ++x) {
+        double* a = acc64 + (size_t)t * C::GT + lane * GX + x;
+        double* b = acc64 + (size_t)(TB + t) * C::GT + lane * GX + x;
+        *a += (double)accA[x][t];
+        *b += (double)accB[x][t];
+        accA[x][t] = 0.0f;
+        accB[x][t] = 0.0f;
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < GX; ++x) {
+      acc64[(size_t)(2 * TB) * C::GT + lane * GX + x] += (double)accC[x];
+      accC[x] = 0.0f;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&flush_bar[(warp + 1) % kConsumerWarps]);
+  };
+
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    const Item it = decode_item(p, item);
+    const MomSide& s = p.side[it.side];
+    const bool do_counts = (it.bg == 0);
+    float a[GX];
+#pragma unroll
+    for (int x = 0; x < GX; ++x) {
+      long long g = (long long)it.gt * C::GT + lane * GX + x;
+      a[x] = g < p.n_genes ? s.pilot[g] : 0.0f;
+    }
+    int cur_win = -1;
+    int since_flush = 0;
+    for (int tile = 0; tile < it.n_tiles; ++tile) {
+      mbar_wait(&full_bar[slot], phase);
+      const float* xt = reinterpret_cast<const float*>(stage_base + (size_t)slot * C::STAGE_BYTES);
+      const float* wt = xt + kCellTile * C::GT;
+#pragma unroll(kCellUnroll)
+      for (int cc = 0; cc < kCellsPerWarp; ++cc) {
+        const int cell = warp * kCellsPerWarp + cc;
+        float w[C::RF];
+        const float4* wrow = reinterpret_cast<const float4*>(wt + cell * C::RF);
+#pragma unroll
+        for (int q = 0; q < C::RF / 4; ++q) {
+          float4 v = wrow[q];
+          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+        float xv[GX];
+        if constexpr (GX == 2) {
+          float2 v = *reinterpret_cast<const float2*>(xt + cell * C::GT + lane * 2);
+          xv[0] = v.x; xv[1] = v.y;
+        } else {
+          xv[0] = xt[cell * C::GT + lane];
+        }
+        const int win = __float_as_int(w[TB + 1]);
+        if (win != cur_win) {  // warp-uniform: every lane looks at the same cell
+          if (do_counts && cur_win >= 0) {
+#pragma unroll
+            for (int x = 0; x < GX; ++x)
+              if (cnt[x]) atomicAdd(&cnt_s[cur_win * C::GT + lane * GX + x], cnt[x]);
+          }
+#pragma unroll
+          for (int x = 0; x < GX; ++x) cnt[x] = 0;
+          cur_win = win;
+        }
+#pragma unroll
+        for (int x = 0; x < GX; ++x) {
+          const float d = xv[x] - a[x];
+          const float y = d * d;
+#pragma unroll
+          for (int t = 0; t < TB; ++t) {
+            accA[x][t] = fmaf(w[t], d, accA[x][t]);
+            accB[x][t] = fmaf(w[t], y, accB[x][t]);
+          }
+          accC[x] = fmaf(w[TB], d, accC[x]);
+          cnt[x] += (xv[x] != 0.0f) ? 1 : 0;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence_block();
+        if (atomicAdd(&done[slot], 1) == kConsumerWarps - 1) {  // last warp out refills the stage
+          done[slot] = 0;
+          __threadfence_block();
+          issue_next(slot);
+          __threadfence_block();
+        }
+      }
+      if (++slot == n_stages) { slot = 0; phase ^= 1; }
+      if (++since_flush == kFlushStages) { flush(); since_flush = 0; }
+    }
+    flush();  // every warp flushes exactly once more per item, keeping the token ring in step
+    if (do_counts && cur_win >= 0) {
+#pragma unroll
+      for (int x = 0; x < GX; ++x)
+        if (cnt[x]) atomicAdd(&cnt_s[cur_win * C::GT + lane * GX + x], cnt[x]);
+    }
+#pragma unroll
+    for (int x = 0; x < GX; ++x) cnt[x] = 0;
+    consumer_bar_sync();
+    // write this item's sums to its slot of the partial buffers and clear the accumulators
+    {
+      const int tid = threadIdx.x;
+      const int T = p.n_bins;
+      const long long g0 = (long long)it.gt * C::GT;
+      double* pf = s.part_f64 + (size_t)it.split * (2 * T + 1) * p.g_stride;
+      for (int k = tid; k < C::NQ * C::GT; k += kConsumerWarps * 32) {
+        const int q = k / C::GT, gl = k % C::GT;
+        const long long g = g0 + gl;
+        int row = -1;
+        if (q < TB) { int t = it.bg * TB + q; if (t < T) row = t; }
+        else if (q < 2 * TB) { int t = it.bg * TB + (q - TB); if (t < T) row = T + t; }
+        else if (do_counts) row = 2 * T;
+        if (row >= 0 && g < p.n_genes) pf[(size_t)row * p.g_stride + g] = acc64[k];
+        acc64[k] = 0.0;
+      }
+      if (do_counts) {
+        int32_t* pi = s.part_i32 + (size_t)it.split * T * p.g_stride;
+        for (int k = tid; k < T * C::GT; k += kConsumerWarps * 32) {
+          const int q = k / C::GT, gl = k % C::GT;
+          const long long g = g0 + gl;
+          if (g < p.n_genes) pi[(size_t)q * p.g_stride + g] = cnt_s[k];
+          cnt_s[k] = 0;
+        }
+      }
+    }
+    consumer_bar_sync();
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    G2G_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      g2g_set_error("cuTensorMapEncodeTiled not available from the driver");
+      return G2G_ERR_CUDA;
+    }
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return G2G_OK;
+}
+
+template <int TB, int GX>
+int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
+  using C = Cfg<TB, GX>;
+  EncodeTiledFn encode;
+  int rc = get_encode_fn(&encode);
+  if (rc != G2G_OK) return rc;
+  for (int s = 0; s < p.n_sides; ++s) {
+    cuuint64_t gdim[2] = {(cuuint64_t)p.n_genes, (cuuint64_t)sides[s].n_cells};
+    cuuint64_t gstride[1] = {(cuuint64_t)sides[s].ldx * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)C::GT, (cuuint32_t)kCellTile};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sides[s].X), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g2g_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+      return G2G_ERR_CUDA;
+    }
+  }
+  p.n_gtiles = (int)g2g_ceil_div(p.n_genes, C::GT);
+  int items = 0;
+  for (int s = 0; s < p.n_sides; ++s) {
+    p.side[s].item_base = items;
+    items += p.n_groups * p.side[s].n_split * p.n_gtiles;
+  }
+  p.n_items = items;
+
+  int dev = 0, n_sm = 0;
+  G2G_CUDA_TRY(cudaGetDevice(&dev));
+  G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const size_t fixed = (size_t)C::NQ * C::GT * 8 + (size_t)p.n_bins * C::GT * 4 + (8 + kConsumerWarps) * 8 + (8 + 2) * 4 + 128;
+  // as many stages (<= 8, >= 2) as fit the shared memory of G2G_MOM_MIN_BLOCKS CTAs per SM
+  int stages = 8;
+  const size_t budget = (size_t)(G2G_MOM_MIN_BLOCKS >= 2 ? 110 : 200) * 1024;
+  while (stages > 2 && fixed + (size_t)stages * C::STAGE_BYTES > budget) --stages;
+  p.n_stages = stages;
+  const size_t smem = fixed + (size_t)stages * C::STAGE_BYTES;
+  G2G_CUDA_TRY(cudaFuncSetAttribute(moments_kernel<TB, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int occ = 0;
+  G2G_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, moments_kernel<TB, GX>, kThreads, smem));
+  if (occ < 1) {
+    g2g_set_error("moments kernel does not fit on an SM (smem %zu bytes)", smem);
+    return G2G_ERR_UNSUPPORTED;
+  }
+  int grid = n_sm * occ;
+  if (grid > items) grid = items;
+  moments_kernel<TB, GX><<<grid, kThreads, smem, stream>>>(p);
+  G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+
+#define G2G_CASE2(TBV) case TBV: return launch_moments<TBV, 2>(p, sides, stream);
+#define G2G_CASE1(TBV) case TBV: return launch_moments<TBV, 1>(p, sides, stream);
+
+int dispatch_moments(MomParams& p, const g2g_side_t* sides, int bins_per_group, cudaStream_t stream) {
+  switch (bins_per_group) {
+    G2G_CASE2(1) G2G_CASE2(2) G2G_CASE2(3) G2G_CASE2(4) G2G_CASE2(5) G2G_CASE2(6) G2G_CASE2(7)
+    G2G_CASE2(8) G2G_CASE2(9) G2G_CASE2(10) G2G_CASE2(11) G2G_CASE2(12) G2G_CASE2(13) G2G_CASE2(14)
+    G2G_CASE2(15) G2G_CASE2(16) G2G_CASE2(17) G2G_CASE2(18) G2G_CASE2(19) G2G_CASE2(20) G2G_CASE2(21)
+    G2G_CASE2(22) G2G_CASE2(23) G2G_CASE2(24) G2G_CASE2(25) G2G_CASE2(26) G2G_CASE2(27) G2G_CASE2(28)
+    G2G_CASE1(29) G2G_CASE1(30) G2G_CASE1(31) G2G_CASE1(32) G2G_CASE1(33) G2G_CASE1(34) G2G_CASE1(35)
+    G2G_CASE1(36) G2G_CASE1(37) G2G_CASE1(38) G2G_CASE1(39) G2G_CASE1(40) G2G_CASE1(41) G2G_CASE1(42)
+    G2G_CASE1(43) G2G_CASE1(44) G2G_CASE1(45) G2G_CASE1(46) G2G_CASE1(47) G2G_CASE1(48) G2G_CASE1(49)
+    G2G_CASE1(50) G2G_CASE1(51) G2G_CASE1(52) G2G_CASE1(53) G2G_CASE1(54) G2G_CASE1(55) G2G_CASE1(56)
+    default:
+      g2g_set_error("bins_per_group %d has no compiled kernel", bins_per_group);
+      return G2G_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace
+
+extern "C" int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                           int32_t n_bins, void* stream) {
+  G2G_REQUIRE(sides != nullptr && n_sides >= 1 && n_sides <= kMaxSides, "n_sides must be 1 or 2");
+  G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
+  G2G_REQUIRE(n_genes >= 1 && g_stride >= n_genes, "bad gene counts");
+  G2G_REQUIRE(n_genes < (1ll << 31), "n_genes too large");
+  G2GTiling t = g2g_tiling(n_bins);
+  MomParams p;
+  p.n_genes = n_genes; p.g_stride = g_stride; p.n_sides = n_sides; p.n_bins = n_bins; p.n_groups = t.n_groups;
+  for (int s = 0; s < n_sides; ++s) {
+    const g2g_side_t& in = sides[s];
+    G2G_REQUIRE(in.X && in.wtab && in.pilot && in.part_f64 && in.part_i32, "null pointer in side");
+    G2G_REQUIRE(in.n_cells >= 1 && in.n_cells < (1ll << 31), "n_cells out of range");
+    G2G_REQUIRE(in.ldx >= n_genes && in.ldx % 4 == 0, "ldx must be >= n_genes and a multiple of 4 (16-byte rows for TMA)");
+    G2G_REQUIRE(((uintptr_t)in.X & 15) == 0, "X must be 16-byte aligned");
+    G2G_REQUIRE(((uintptr_t)in.wtab & 15) == 0, "wtab must be 16-byte aligned");
+    g2g_layout_t lay;
+    int rc = g2g_layout(in.n_cells, n_bins, &lay);
+    if (rc != G2G_OK) return rc;
+    p.side[s].wtab = in.wtab; p.side[s].pilot = in.pilot;
+    p.side[s].part_f64 = in.part_f64; p.side[s].part_i32 = in.part_i32;
+    p.side[s].n_pad = lay.n_pad; p.side[s].cells_per_item = lay.cells_per_item;
+    p.side[s].n_split = (int)lay.n_split;
+  }
+  return dispatch_moments(p, sides, t.bins_per_group, (cudaStream_t)stream);
+}

@@ -1,0 +1,265 @@
+"""Batched device pipeline behind ``Main.RefQueryAligner``: all genes of one (reference, query)
+pair go through five kernel launches of ``libg2g.so``.
+
+PyTorch is used for device memory, streams and (multi-GPU) ``torch.distributed`` only; every
+kernel is hand-written CUDA behind the C ABI in ``include/g2g.h``.
+"""
+import ctypes
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import Side, c_f64
+
+N_SAMPLES = 50  # reference: generate_random_dataset(50, ...)  TimeSeriesPreprocessor.py:179
+
+
+def epsilon_table(n_bins, n_samples=N_SAMPLES, seed=1):
+    """The fixed standard-normal table behind every interpolated bin of the reference.
+
+    The reference re-seeds torch with 1 at the top of each ``interpolate_gene_v2`` call
+    (TimeSeriesPreprocessor.py:184) and then draws ``n_samples`` scalar normals per bin
+    (MyFunctions.py:64-67), so ``data_bins[t][n] = mean_t + eps[t, n] * std_t`` with one table
+    shared by all genes.  A private generator seeded the same way gives the same mt19937 stream
+    without touching the global RNG state.
+    """
+    gen = torch.Generator(device="cpu")
+    gen.manual_seed(seed)
+    zero = torch.zeros((), dtype=torch.float64)
+    one = torch.ones((), dtype=torch.float64)
+    out = np.empty((n_bins, n_samples), dtype=np.float64)
+    for t in range(n_bins):
+        for n in range(n_samples):
+            out[t, n] = float(torch.normal(zero, one, generator=gen))
+    return out
+
+
+def transition_costs(free_params=(0.99, 0.1, 0.7), prohibit_case=False):
+    """-ln of the five-state machine's transition probabilities, ``I[to, from]`` with states in
+    M, W, V, D, I order (reference: FiveStateMachine.__init__, OrgAlign.py:20-97).  Computed on
+    the host with numpy so the table is bit-identical to the reference's."""
+    p_mm, p_ii, p_mi = (float(v) for v in free_params)
+    k = (1.0 - p_mm) / 4.0
+    p_vi = 0.0 if prohibit_case else p_ii
+    p_wi = 0.0
+    p_di = 1.0 - p_ii - p_mi - p_wi - p_vi
+    prob = np.array([
+        # from:  M     W     V     D      I
+        [p_mm, k, k, p_mi, p_mi],      # to M   (I_mm, I_mw, I_mv, I_md, I_mi)
+        [k, p_mm, k, p_vi, p_wi],      # to W   (.., I_wd = -ln P_vi, I_wi = -ln 0)
+        [k, k, p_mm, 0.0, p_vi],       # to V   (.., I_vd = -ln 0,   I_vi)
+        [k, k, k, p_ii, p_di],         # to D   (.., I_dd, I_di)
+        [k, k, k, p_di, p_ii],         # to I   (.., I_id, I_ii)
+    ], dtype=np.float64)
+    with np.errstate(divide="ignore"):
+        return -np.log(prob)
+
+
+def start_costs():
+    """(-ln ProbI, -ln ProbD) of the DP borders (OrgAlign.py:274-276, 304, 324) and -ln 0.99 of
+    the first match cell (OrgAlign.py:336, 345)."""
+    prob_m = 0.9999
+    prob_i = (1.0 - prob_m) / 2.0
+    return np.array([-np.log(prob_i), -np.log(prob_i), -np.log(0.99)], dtype=np.float64)
+
+
+def model_constant(n_samples=N_SAMPLES):
+    """ln(5/(36 sqrt 3)) + ln(15*3) + 0.5 ln(2 N^2): the sigma-independent part of the MML model
+    cost (MyFunctions.py:21-29, 41, 46)."""
+    return math.log(5 / (36 * math.sqrt(3))) + math.log(45.0) + 0.5 * math.log(2.0 * n_samples ** 2)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class DeviceSide:
+    """Device-resident state of one dataset: packed expression matrix, weight table, workspaces."""
+
+    def __init__(self, X, tau_sorted, n_genes, n_bins, denom, device):
+        self.X = X  # f32 [n_cells, ld] time-sorted, ld % 4 == 0
+        self.n_cells = int(X.shape[0])
+        self.ld = int(X.shape[1])
+        self.n_genes = n_genes
+        lay = _lib.layout(self.n_cells, n_bins)
+        self.layout = lay
+        self.tau = torch.as_tensor(np.ascontiguousarray(tau_sorted, dtype=np.float64)).to(device)
+        self.denom = torch.as_tensor(np.ascontiguousarray(denom, dtype=np.float64)).to(device)
+        self.wtab = torch.empty(lay.n_groups * lay.n_pad * lay.row_floats, dtype=torch.float32, device=device)
+        self.sum_w = torch.empty(n_bins, dtype=torch.float64, device=device)
+        ws = _lib.load().g2g_weights_workspace_bytes(self.n_cells, n_bins)
+        self.ws = torch.empty((ws + 7) // 8, dtype=torch.float64, device=device)
+        self.ws_bytes = ws
+        self.pilot = torch.empty(n_genes, dtype=torch.float32, device=device)
+        self.g_stride = n_genes
+        self.part_f64 = torch.empty(lay.n_split * (2 * n_bins + 1) * n_genes, dtype=torch.float64, device=device)
+        self.part_i32 = torch.empty(lay.n_split * n_bins * n_genes, dtype=torch.int32, device=device)
+
+    def c_side(self):
+        return Side(self.X.data_ptr(), self.n_cells, self.ld, self.wtab.data_ptr(), self.pilot.data_ptr(),
+                    self.part_f64.data_ptr(), self.part_i32.data_ptr())
+
+
+def pack_dense(X, row_order, gene_idx, device):
+    """Device copy of ``X[row_order][:, gene_idx]`` as f32 with 16-byte aligned rows
+    (``g2g_pack_rows``).  ``X`` may be a host array / tensor (copied first) or a CUDA tensor."""
+    lib = _lib.load()
+    if not torch.is_tensor(X):
+        X = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32))
+    if X.dtype != torch.float32:
+        X = X.to(torch.float32)
+    Xd = X.to(device, non_blocking=True).contiguous()
+    n_cells, ld_src = int(Xd.shape[0]), int(Xd.shape[1])
+    n_genes = ld_src if gene_idx is None else len(gene_idx)
+    ld = (n_genes + 3) // 4 * 4
+    identity_rows = row_order is None
+    if identity_rows and gene_idx is None and ld == ld_src:
+        return Xd
+    out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
+    ro = None if identity_rows else torch.as_tensor(np.ascontiguousarray(row_order, dtype=np.int64)).to(device)
+    gi = None if gene_idx is None else torch.as_tensor(np.ascontiguousarray(gene_idx, dtype=np.int32)).to(device)
+    _lib.check(lib.g2g_pack_rows(_ptr(Xd), n_cells, n_genes, ld_src, _ptr(ro), _ptr(gi), _ptr(out), ld, _stream()),
+               "g2g_pack_rows")
+    return out
+
+
+def pack_csr(csr, row_order, gene_idx, n_all_genes, device):
+    """Densify a scipy CSR matrix (cells x all genes) on the device (``g2g_pack_csr``): only the
+    non-zeros cross PCIe."""
+    lib = _lib.load()
+    n_cells = csr.shape[0]
+    n_genes = n_all_genes if gene_idx is None else len(gene_idx)
+    ld = (n_genes + 3) // 4 * 4
+    indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device, non_blocking=True)
+    indices = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device, non_blocking=True)
+    data = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(device, non_blocking=True)
+    col_map = None
+    if gene_idx is not None:
+        cm = np.full(n_all_genes, -1, dtype=np.int32)
+        cm[np.asarray(gene_idx)] = np.arange(n_genes, dtype=np.int32)
+        col_map = torch.from_numpy(cm).to(device)
+    ro = None if row_order is None else torch.as_tensor(np.ascontiguousarray(row_order, dtype=np.int64)).to(device)
+    out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
+    _lib.check(lib.g2g_pack_csr(_ptr(indptr), _ptr(indices), _ptr(data), n_cells, _ptr(ro), _ptr(col_map),
+                                _ptr(out), ld, _stream()), "g2g_pack_csr")
+    return out
+
+
+class AlignmentEngine:
+    """Runs the whole hot path for one (reference, query) pair of packed device matrices.
+
+    ``run()`` enqueues K0 (weights) + K1a (pilot) + K1 (moments) + K3 (fix-up / trends) + K4
+    (cost + DP + traceback) on the current stream and returns the device result tensors.
+    """
+
+    def __init__(self, X_ref, tau_ref, X_query, tau_query, n_genes, n_bins, denom_ref, denom_query,
+                 free_params=(0.99, 0.1, 0.7), device=None):
+        self.lib = _lib.load()
+        _lib.check(self.lib.g2g_check_device(), "g2g_check_device")
+        self.device = device if device is not None else X_ref.device
+        self.n_genes, self.n_bins = int(n_genes), int(n_bins)
+        T, G, dev = self.n_bins, self.n_genes, self.device
+        self.ref = DeviceSide(X_ref, tau_ref, G, T, denom_ref, dev)
+        self.query = DeviceSide(X_query, tau_query, G, T, denom_query, dev)
+        self.points_host = np.linspace(0, 1, T)  # TimeSeriesPreprocessor.py:23
+        self.eps = epsilon_table(T)
+        f64 = dict(dtype=torch.float64, device=dev)
+        self.points = torch.as_tensor(self.points_host).to(dev)
+        self.eps_mean = torch.as_tensor(self.eps.mean(axis=1)).to(dev)
+        self.eps_std = torch.as_tensor(self.eps.std(axis=1)).to(dev)
+        self.set_state_params(free_params)
+        self.start = start_costs()
+        self.c_model = model_constant()
+        self.musigma = torch.empty((G, 4, T), **f64)
+        self.trends = torch.empty((G, 4, T), **f64)
+        self.nnz = torch.empty((G, 2), dtype=torch.int32, device=dev)
+        self.flags = torch.empty(G, dtype=torch.int32, device=dev)
+        self.align_str = torch.empty((G, 2 * T), dtype=torch.uint8, device=dev)
+        self.align_len = torch.empty(G, dtype=torch.int32, device=dev)
+        self.opt_cost = torch.empty(G, **f64)
+        self.l_states = torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev)
+        self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
+        self.launches_per_run = 0
+
+    def set_state_params(self, free_params):
+        self.free_params = tuple(float(v) for v in free_params)
+        self.trans = transition_costs(self.free_params)
+
+    # -- stages -----------------------------------------------------------------------------
+    def run_interpolation(self):
+        lib, T, G = self.lib, self.n_bins, self.n_genes
+        st = _stream()
+        n = 0
+        for s in (self.ref, self.query):
+            _lib.check(lib.g2g_weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
+                                       _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
+            _lib.check(lib.g2g_pilot_mean(_ptr(s.X), s.n_cells, G, s.ld, _ptr(s.pilot), st), "g2g_pilot_mean")
+            n += 2
+        _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+        _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
+                                        _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
+                                        _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), st), "g2g_fixup_trends")
+        return n + 2
+
+    def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None):
+        """K4 on all genes (or ``gene_slice``).  ``dump=True`` also returns the dense matrices."""
+        lib, T = self.lib, self.n_bins
+        trends = self.trends if trends is None else trends
+        if gene_slice is not None:
+            trends = trends[gene_slice].contiguous()
+        G = int(trends.shape[0])
+        dev = self.device
+        if gene_slice is None and not dump and cost_in is None:
+            out = dict(align_str=self.align_str, align_len=self.align_len, opt_cost=self.opt_cost,
+                       l_states=self.l_states)
+        else:
+            out = dict(align_str=torch.empty((G, 2 * T), dtype=torch.uint8, device=dev),
+                       align_len=torch.empty(G, dtype=torch.int32, device=dev),
+                       opt_cost=torch.empty(G, dtype=torch.float64, device=dev),
+                       l_states=torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev))
+        cost_out = mats = bp = l_out = None
+        if dump:
+            cost_out = torch.empty((G, T, T), dtype=torch.float64, device=dev)
+            mats = torch.empty((G, 5, T + 1, T + 1), dtype=torch.float64, device=dev)
+            bp = torch.empty((G, 5, T + 1, T + 1), dtype=torch.int8, device=dev)
+            l_out = torch.empty((G, T + 1, T + 1), dtype=torch.float64, device=dev)
+            out.update(cost=cost_out, mats=mats, bp=bp, L=l_out)
+        trans = (c_f64 * 25)(*self.trans.reshape(-1).tolist())
+        start = (c_f64 * 3)(*self.start.tolist())
+        _lib.check(lib.g2g_cost_dp(_ptr(trends), G, T, trans, start, self.c_model, N_SAMPLES, _ptr(cost_in),
+                                   _ptr(out["align_str"]), _ptr(out["align_len"]), _ptr(out["opt_cost"]),
+                                   _ptr(out["l_states"]), _ptr(cost_out), _ptr(mats), _ptr(bp), _ptr(l_out),
+                                   _stream()), "g2g_cost_dp")
+        return out
+
+    def time_moments(self, start_event, end_event):
+        """Launch K1 alone between two CUDA events on the current stream (roofline measurement;
+        the weight tables and pilot values of the last run are reused)."""
+        start_event.record()
+        _lib.check(self.lib.g2g_moments(self._sides, 2, self.n_genes, self.n_genes, self.n_bins, _stream()),
+                   "g2g_moments")
+        end_event.record()
+
+    def run(self):
+        n = self.run_interpolation()
+        self.run_dp()
+        self.launches_per_run = n + 1
+        return self
+
+    def results_to_host(self):
+        """One device->host transfer per result array (pinned staging, then a single sync)."""
+        keys = ("musigma", "trends", "nnz", "flags", "align_str", "align_len", "opt_cost", "l_states")
+        host = {}
+        for k in keys:
+            t = getattr(self, k)
+            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+            h.copy_(t, non_blocking=True)
+            host[k] = h
+        torch.cuda.current_stream().synchronize()
+        return {k: v.numpy() for k, v in host.items()}

@@ -1,0 +1,187 @@
+/*
+ * libg2g -- C ABI of the B200-native Genes2Genes per-gene alignment hot path.
+ *
+ * The reference (Teichlab/Genes2Genes v0.2.0) is pure Python and has no FFI layer; its seam for
+ * this path is the Python API of genes2genes/Main.py (RefQueryAligner.__init__ :196-221,
+ * align_all_pairs :434-457).  This header is the boundary a maintainer would bind from that
+ * class with ctypes.  Each entry point names the reference code it replaces.
+ *
+ * Conventions
+ *   - plain C types only; every data pointer is a DEVICE pointer owned by the caller;
+ *     the library allocates no user-visible memory (workspaces are caller-provided);
+ *   - every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns
+ *     without synchronising; 0 = success, negative = error (g2g_last_error() has the text);
+ *   - thread-compatible: no global state except a thread-local error string;
+ *   - sm_100a (B200) only; there is no CPU fallback.
+ */
+#ifndef G2G_H_
+#define G2G_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define G2G_VERSION 100          /* 0.1.0 */
+#define G2G_MAX_BINS 128         /* n_interpolation_points supported: 2..128 */
+#define G2G_CELL_TILE 64         /* rows of X per pipeline stage; weight tables are padded to it */
+
+enum {
+  G2G_OK = 0,
+  G2G_ERR_ARG = -1,              /* bad argument (sizes, alignment, null pointer) */
+  G2G_ERR_CUDA = -2,             /* a CUDA runtime / driver call failed */
+  G2G_ERR_UNSUPPORTED = -3       /* device is not sm_100 or shape outside compiled range */
+};
+
+/* per-gene status bits written by g2g_fixup_trends (flags[g]) */
+enum {
+  G2G_FLAG_BRANCH_MASK = 0x3,    /* 0 both ~zero, 1 ref ~zero, 2 query ~zero, 3 both expressed (Main.py:344-376) */
+  G2G_FLAG_REGION_REF = 0x4,     /* a low-expression region override fired on the reference side */
+  G2G_FLAG_REGION_QUERY = 0x8,   /* ... on the query side */
+  G2G_FLAG_BAD_SIGMA = 0x10      /* a final std is <= 0 or not finite: the reference raises here
+                                    (torch Normal validation, MyFunctions.py:64) */
+};
+
+int g2g_version(void);
+const char* g2g_last_error(void);
+/* 0 when the current device is compute capability 10.x, else G2G_ERR_UNSUPPORTED. */
+int g2g_check_device(void);
+
+/* How the interpolation kernels tile `n_bins`: bins are split into `n_groups` groups of
+ * `bins_per_group` (last group zero-padded); one row of the weight table holds, per group,
+ * `row_floats` floats = [w_0 .. w_{bins_per_group-1}, valid, window_id(int bits), 0-pad]. */
+typedef struct {
+  int32_t n_groups;
+  int32_t bins_per_group;
+  int32_t row_floats;            /* multiple of 4 */
+  int32_t genes_per_tile;        /* genes handled by one thread block (32 or 64) */
+  int64_t n_pad;                 /* n_cells rounded up to G2G_CELL_TILE */
+  int64_t cells_per_item;        /* cell range of one work item (multiple of G2G_CELL_TILE); depends
+                                    on (n_cells, n_bins) only, never on n_genes => shard-invariant sums */
+  int64_t n_split;               /* ceil(n_pad / cells_per_item) */
+} g2g_layout_t;
+
+int g2g_layout(int64_t n_cells, int32_t n_bins, g2g_layout_t* out);
+
+/* ---------------------------------------------------------------------------------------------
+ * g2g_pack_rows / g2g_pack_csr -- bring an expression matrix into the layout K1 streams.
+ * Replaces `adata[:, gene_list]` (Main.py:226-227), the pseudotime sort (TimeSeriesPreprocessor.py:20)
+ * and `adata.X.todense()` (Main.py:232,238; TSP.py:28) for device-resident data.
+ *   dst[r][g] = src[row_order[r]][gene_idx[g]]   (row_order / gene_idx may be null = identity);
+ *   columns n_genes..ld_dst-1 of dst are zero filled.  g2g_pack_csr scatters a CSR matrix
+ *   (cells x all genes; indptr i64, indices i32, data f32) into a zeroed dst, mapping source column c
+ *   to col_map[c] (-1 = gene not selected; null = identity).
+ */
+int g2g_pack_rows(const float* src, int64_t n_cells, int64_t n_genes, int64_t ld_src,
+                  const int64_t* row_order, const int32_t* gene_idx, float* dst, int64_t ld_dst,
+                  void* stream);
+int g2g_pack_csr(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_cells,
+                 const int64_t* row_order, const int32_t* col_map, float* dst, int64_t ld_dst,
+                 void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K0  g2g_weights -- Gaussian-kernel cell weights for one dataset.
+ * Replaces TrajectoryInterpolator.compute_abs_timediff_mat / compute_Weight_matrix
+ * (TimeSeriesPreprocessor.py:44-51, 122-133) and the window membership test of
+ * RefQueryAligner.check_inconsistent_zero_region (Main.py:298-299).
+ *   tau[n_cells]        f64 pseudotimes (any order; the sums are order independent)
+ *   points[n_bins]      f64 interpolation points (np.linspace(0,1,n_bins), TSP.py:23)
+ *   denom[n_bins]       f64 kernel denominators: kernel_WINDOW_SIZE**2 everywhere (TSP.py:127) or
+ *                       the adaptive per-bin values (TSP.py:88-119, 125)
+ *   wtab                f32 out, [n_groups][n_pad][row_floats]; w = exp(-(tau-p_t)^2/denom_t) computed
+ *                       in f64 and rounded once; rows >= n_cells are zero with window -1
+ *   sum_w[n_bins]       f64 out, sum over cells of the f64 weights (np.sum(row), TSP.py:164)
+ *   workspace           >= g2g_weights_workspace_bytes() bytes, 8-byte aligned
+ */
+size_t g2g_weights_workspace_bytes(int64_t n_cells, int32_t n_bins);
+int g2g_weights(const double* tau, int64_t n_cells, const double* points, const double* denom,
+                int32_t n_bins, float* wtab, double* sum_w, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1a g2g_pilot_mean -- per-gene shift value a[g] (mean of a fixed strided sample of <= 64 rows).
+ * Any value close to the gene's mean works: it only conditions the single-pass variance
+ *   sum w (x - xbar)^2 = sum w (x-a)^2 - 2 (xbar-a) sum w (x-a) + (xbar-a)^2 sum w
+ * which g2g_fixup_trends evaluates in f64 (the reference takes the variance around the
+ * un-weighted whole-gene mean, TSP.py:171-172).
+ */
+int g2g_pilot_mean(const float* X, int64_t n_cells, int64_t n_genes, int64_t ldx, float* pilot,
+                   void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  g2g_moments -- single pass over the expression matrices of up to two datasets.
+ * Replaces the per-gene, per-bin reductions of compute_stat (TSP.py:161-174: np.sum(row),
+ * np.dot(row, x), np.dot(row, (x - mean)**2)), Utils.csr_mat_col_densify (Utils.py:6-12),
+ * np.count_nonzero (Main.py:344,350,363) and the per-window counts of Main.py:298-301.
+ *   X            f32 [n_cells][ldx] row major (cells x genes); ldx % 4 == 0 and X 16-byte aligned
+ *                (the matrix is streamed with TMA)
+ *   wtab, pilot  from g2g_weights / g2g_pilot_mean
+ *   part_f64     f64 out [n_split][2*n_bins+1][g_stride]: per split, sum w(x-a) per bin,
+ *                sum w(x-a)^2 per bin, sum (x-a)
+ *   part_i32     i32 out [n_split][n_bins][g_stride]: nnz per window k (p_k <= tau < p_{k+1}) for
+ *                k < n_bins-1, and at index n_bins-1 the nnz of cells outside every window
+ *   g_stride     >= n_genes
+ * Products are f32 (exact inputs, weights rounded once), summed in f32 over at most 64 cells and
+ * then in f64, in an order fixed by (n_cells, n_bins) alone.
+ */
+typedef struct {
+  const float* X;
+  int64_t n_cells;
+  int64_t ldx;
+  const float* wtab;
+  const float* pilot;
+  double* part_f64;
+  int32_t* part_i32;
+} g2g_side_t;
+
+int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                int32_t n_bins, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3  g2g_fixup_trends -- per gene: finish the moments, apply the low-expression policy, make trends.
+ * Replaces the arithmetic of compute_stat (TSP.py:166-177), RefQueryAligner.run_interpolation
+ * (Main.py:344-406), check_inconsistent_zero_region / extract_significant_regions_only
+ * (Main.py:261-304) and SummaryTimeSeries mean_trend / std_trend (TSP.py:205-206, through the
+ * fixed epsilon table: mean(mu + sigma*eps_t) , std(mu + sigma*eps_t)).
+ *   side[0] = reference (S), side[1] = query (T): the part_* / pilot / n_cells of g2g_moments
+ *   sum_w_{ref,query}[n_bins], points[n_bins], eps_mean[n_bins], eps_std[n_bins]   f64
+ *   musigma   f64 out [n_genes][4][n_bins]: intpl_means_S, intpl_stds_S, intpl_means_T, intpl_stds_T
+ *   trends    f64 out [n_genes][4][n_bins]: mean_trend_S, std_trend_S, mean_trend_T, std_trend_T
+ *   nnz       i32 out [n_genes][2]
+ *   flags     i32 out [n_genes]  (G2G_FLAG_*)
+ */
+int g2g_fixup_trends(const g2g_side_t* sides, const double* sum_w_ref, const double* sum_w_query,
+                     const double* points, const double* eps_mean, const double* eps_std,
+                     int64_t n_genes, int64_t g_stride, int32_t n_bins, double* musigma,
+                     double* trends, int32_t* nnz, int32_t* flags, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K4  g2g_cost_dp -- MML match cost + five-state DP + traceback + landscape, one warp per gene.
+ * Replaces DP5.compute_cell + MyFunctions.run_dist_compute_v3 (OrgAlign.py:471-503,
+ * MyFunctions.py:10-50; closed form in the trend vectors), DP5.init / run_optimal_alignment
+ * (OrgAlign.py:272-468), DP5.backtrack (:539-607) and AlignmentLandscape.collate_fwd (:732-747).
+ *   trends      f64 [n_genes][4][n_bins] (as written by g2g_fixup_trends)
+ *   trans[25]   f64 HOST pointer: transition costs I[to][from], states M,W,V,D,I (FiveStateMachine,
+ *               OrgAlign.py:20-97); copied into the launch
+ *   start[3]    f64 HOST pointer: -ln(ProbI), -ln(ProbD) (OrgAlign.py:274-276,304,324), -ln(0.99) (:336,345)
+ *   c_model     ln(5/(36 sqrt 3)) + ln 45 + 0.5 ln(2 N^2), n_samples = N = 50 (MyFunctions.py:21-29,41,46)
+ *   cost_in     optional f64 [n_genes][n_bins][n_bins] (query bin i, ref bin j): use instead of computing
+ *   align_str   u8 out [n_genes][2*n_bins], zero padded; align_len i32 out [n_genes]
+ *   opt_cost    f64 out [n_genes]
+ *   l_states    u8 out [n_genes][(n_bins+1)^2]  argmin over (M,W,V,D,I) per DP cell (:743-747)
+ *   optional dense dumps (null to skip): cost_out f64 [n_genes][n_bins][n_bins];
+ *   mats_out f64 [n_genes][5][(n_bins+1)^2]; bp_out i8 [n_genes][5][(n_bins+1)^2] (predecessor state,
+ *   -1 where the reference defines none); l_out f64 [n_genes][(n_bins+1)^2]
+ * All DP arithmetic is f64 adds / compares in the reference's order: bit-exact given equal costs.
+ */
+int g2g_cost_dp(const double* trends, int64_t n_genes, int32_t n_bins, const double* trans,
+                const double* start, double c_model, int32_t n_samples, const double* cost_in,
+                uint8_t* align_str, int32_t* align_len, double* opt_cost, uint8_t* l_states,
+                double* cost_out, double* mats_out, int8_t* bp_out, double* l_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* G2G_H_ */

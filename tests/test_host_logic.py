@@ -1,0 +1,188 @@
+"""CPU tests of the host side: alignment-string post-processing against the reference's golden
+outputs, host tables against the oracle, the C-ABI surface, layout rules and the gloo gather."""
+import ctypes
+import json
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from genes2genes_b200 import Main, OrgAlign, engine, _lib
+from genes2genes_b200.TimeSeriesPreprocessor import SummaryTimeSeries, TrajectoryInterpolator
+from oracle import g2g_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FIXTURES = ["tutorial_ref_T14.npz", "synthetic_sparse_ref.npz", "synthetic_T13_ref.npz", "tutorial_ref_adaptive.npz"]
+
+
+@pytest.mark.parametrize("name", FIXTURES)
+def test_string_postprocessing_matches_reference(golden_dir, name):
+    ref = np.load(os.path.join(golden_dir, name))
+    for g, s in enumerate(str(x) for x in ref["alignment_str"]):
+        vis, col, _ = Main.alignment_visual(s)
+        assert vis == str(ref["al_visual"][g])
+        assert col == str(ref["colored"][g])
+        S, T = Main.matched_time_points(s)
+        assert list(S) == json.loads(str(ref["match_points_S"][g]))
+        assert list(T) == json.loads(str(ref["match_points_T"][g]))
+        assert OrgAlign.legacy_matched_regions(s) == json.loads(str(ref["regions"][g]))
+        assert OrgAlign.path_from_string(s) == json.loads(str(ref["paths"][g]))
+
+
+def test_matched_points_equal_dp_cells_on_random_legal_strings():
+    """For FSA-legal strings the matched bin pairs are the DP cells reached by M/W/V steps
+    (SURVEY.md 8(a) row 14)."""
+    rng = np.random.default_rng(0)
+    for _ in range(3000):
+        n = rng.integers(1, 30)
+        s, prev = [], ""
+        for k in range(n):
+            opts = "MWVDI"
+            if k == 0:
+                opts = "MDI"
+            elif prev == "I":
+                opts = "MVDI"      # I -> W prohibited (P_wi = 0)
+            elif prev == "D":
+                opts = "MWDI"      # D -> V prohibited (P_vd = 0)
+            prev = opts[rng.integers(len(opts))]
+            s.append(prev)
+        s = "".join(s)
+        if s[0] in "WV":
+            continue
+        S, T = Main.matched_time_points(s)
+        cells = OrgAlign.path_from_string(s)[::-1]
+        want = [(c[1] - 1, c[0] - 1) for ch, c in zip(s, cells) if ch in "MWV"]
+        assert list(zip(S.tolist(), T.tolist())) == want, s
+
+
+def test_aligment_obj_fields_from_reference_strings(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
+    eps = engine.epsilon_table(14)
+    pts = np.linspace(0, 1, 14)
+    for g in range(0, 89, 7):
+        S = SummaryTimeSeries("g", ref["intpl_means_S"][g], ref["intpl_stds_S"][g], ref["mean_trend_S"][g],
+                              ref["std_trend_S"][g], pts, eps)
+        T = SummaryTimeSeries("g", ref["intpl_means_T"][g], ref["intpl_stds_T"][g], ref["mean_trend_T"][g],
+                              ref["std_trend_T"][g], pts, eps)
+        dp = OrgAlign.DP5(None, g, S, T, str(ref["alignment_str"][g]), ref["opt_cost"][g], (0.99, 0.1, 0.7))
+        a = Main.AligmentObj(None, g, "g", S, T, dp, OrgAlign.AlignmentLandscape(dp, ref["L_states"][g], 14, 14))
+        assert tuple(a.get_series_match_percentage()) == tuple(ref["match_percentage"][g])
+        assert (np.asarray(a.landscape_obj.L_matrix_states) == ref["L_states"][g].astype("<U1")).all()
+        assert a.fwd_DP.alignment_path == json.loads(str(ref["paths"][g]))
+        if g < ref["data_bins_S"].shape[0]:
+            assert np.array_equal(np.asarray(S.data_bins), ref["data_bins_S"][g])
+            assert np.array_equal(S.Y, ref["data_bins_S"][g].flatten())
+        # DE statistics table (scipy on the host) vs the reference's
+        want = np.asarray(json.loads(str(ref["de_info"][g])))
+        got = a.matched_region_DE_info.values.astype(float)
+        np.testing.assert_allclose(got[:, :4], want[:, :4], rtol=1e-12)
+        np.testing.assert_allclose(got[:, 4], want[:, 4], atol=2e-7)     # Delta = round(cost, 7)
+        np.testing.assert_allclose(got[:, 5:], want[:, 5:], rtol=1e-6, atol=1e-6)
+
+
+def test_host_tables_equal_oracle():
+    assert np.array_equal(engine.transition_costs(), o.transition_table())
+    assert np.array_equal(engine.transition_costs((0.9, 0.2, 0.5), True), o.transition_table((0.9, 0.2, 0.5), True))
+    assert np.array_equal(engine.start_costs(), o.start_costs())
+    assert engine.model_constant() == o.C_MODEL
+    assert np.array_equal(engine.epsilon_table(7), o.epsilon_table(7))
+    fsa = OrgAlign.FiveStateMachine(0.99, 0.1, 0.7)
+    assert fsa.I_di == 2.302585092994045 and fsa.I_ii == 2.3025850929940455 and np.isinf(fsa.I_wi)
+
+
+def test_adaptive_denominators_equal_reference(golden_dir):
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_adaptive.npz"))
+    inp = np.load(os.path.join(golden_dir, "tutorial_inputs.npz"))
+    for side, key in (("ref", "R"), ("query", "Q")):
+        ti = TrajectoryInterpolator(inp["time_" + side], 14, adaptive_kernel=True).run()
+        assert np.array_equal(np.asarray(ti.adaptive_win_denoms), ref["adaptive_win_denoms_" + key])
+        np.testing.assert_allclose(ti.cell_weight_mat.sum(axis=1).values, ref["cell_weight_sum_" + key], rtol=1e-13)
+
+
+def test_c_abi_exports_every_declared_symbol():
+    """libg2g.so loads and exports exactly the entry points include/g2g.h declares."""
+    header = open(os.path.join(ROOT, "include", "g2g.h")).read()
+    declared = set(re.findall(r"\b(g2g_[a-z0-9_]+)\s*\(", header))
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.g2g_version() == 100
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r" T (g2g_[a-z0-9_]+)", out))
+    assert exported == declared
+
+
+def test_layout_depends_on_cells_and_bins_only():
+    lay = _lib.layout(20327, 14)
+    assert lay.n_groups == 1 and lay.bins_per_group == 14 and lay.row_floats == 16 and lay.genes_per_tile == 64
+    assert lay.n_pad == 20352 and lay.cells_per_item % 64 == 0
+    assert lay.n_split == -(-lay.n_pad // lay.cells_per_item)
+    lay = _lib.layout(100000, 50)
+    assert lay.bins_per_group == 50 and lay.genes_per_tile == 32 and lay.row_floats == 52
+    lay = _lib.layout(1000, 100)
+    assert lay.n_groups == 2 and lay.bins_per_group == 50
+    lay = _lib.layout(3, 2)
+    assert lay.n_pad == 64 and lay.n_split == 1
+    bad = _lib.Layout()
+    assert _lib.load().g2g_layout(10, 1, ctypes.byref(bad)) < 0
+    assert b"n_bins" in _lib.load().g2g_last_error()
+
+
+def test_argument_errors_are_reported_without_a_gpu():
+    lib = _lib.load()
+    assert lib.g2g_moments(None, 1, 10, 10, 14, None) < 0
+    assert lib.g2g_cost_dp(None, 1, 300, None, None, 0.0, 50, None, None, None, None, None, None, None, None, None,
+                           None) < 0
+
+
+_GLOO_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+from genes2genes_b200 import distributed as d
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo")
+G, T = 10, 6
+lo, hi = d.shard_range(G, rank, world)
+per = -(-G // world)
+class Src: pass
+src = Src()
+tmpl = d.record_templates(per, T)
+rng = np.random.default_rng(rank)
+for k, (shape, dtype) in tmpl.items():
+    setattr(src, k, torch.from_numpy(rng.integers(0, 100, shape)).to(dtype))
+g = d.ResultGather(src, dst=0)
+g.run()
+if rank == 0:
+    res = g.host_results(per, T)
+    assert len(res) == world
+    for r in range(world):
+        rr = np.random.default_rng(r)
+        for k, (shape, dtype) in tmpl.items():
+            want = torch.from_numpy(rr.integers(0, 100, shape)).to(dtype).numpy()
+            assert np.array_equal(res[r][k], want), (r, k)
+    print("GLOO_OK", d.record_bytes(per, T))
+dist.destroy_process_group()
+"""
+
+
+def test_result_gather_world_size_2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER % ROOT)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         capture_output=True, text=True, timeout=240)
+    assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
+
+
+def test_shard_range_covers_all_genes():
+    from genes2genes_b200 import distributed as d
+    for G in (1, 7, 8, 1371, 20000):
+        for world in (1, 2, 4, 8):
+            spans = [d.shard_range(G, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == G
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
