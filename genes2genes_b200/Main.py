@@ -151,38 +151,73 @@ def matched_time_points(s):
 
 class AligmentObj:
     """Alignment result of one gene (reference: Main.py:33-177; the class name keeps the
-    reference's spelling).  A view over the aligner's batched arrays."""
+    reference's spelling).  A view over the aligner's batched arrays: constructing it costs O(1);
+    ``alignment_str``, ``S``, ``T``, ``fwd_DP``, ``landscape_obj``, the region lists and the match
+    percentages are materialised on first access and then cached as plain attributes."""
 
-    def __init__(self, aligner, gene_idx, gene, S, T, fwd_DP, landscape_obj):
+    _LAZY = {
+        "alignment_str": "_load_str", "fwd_DP": "_load_core", "landscape_obj": "_load_core",
+        "S": "_load_series", "T": "_load_series",
+        "match_regions_S": "_load_regions", "match_regions_T": "_load_regions",
+        "non_match_regions_S": "_load_regions", "non_match_regions_T": "_load_regions",
+        "match_percentage": "compute_series_match_percentage",
+        "match_percentage_S": "compute_series_match_percentage",
+        "match_percentage_T": "compute_series_match_percentage",
+    }
+
+    def __init__(self, aligner, gene_idx, gene, host=None):
         self._aligner = aligner
         self._gene_idx = gene_idx
+        self._host = host
         self.gene = gene
-        self.S = S
-        self.T = T
-        self.alignment_str = fwd_DP.alignment_str
-        self.landscape_obj = landscape_obj
-        self.fwd_DP = fwd_DP
         self.bwd_DP = None
-        regions = fwd_DP.get_matched_regions()
-        self.match_regions_S, self.match_regions_T, self.non_match_regions_S, self.non_match_regions_T = regions
-        self.compute_series_match_percentage()
         self._visual = None
         self._points = None
         self._de = None
+
+    def __getattr__(self, name):
+        loader = AligmentObj._LAZY.get(name)
+        if loader is None:
+            raise AttributeError(name)
+        getattr(self, loader)()
+        return self.__dict__[name]
+
+    def _results(self):
+        return self._aligner._host if self._host is None else self._host
+
+    def _load_str(self):
+        h, idx = self._results(), self._gene_idx
+        self.alignment_str = h["align_str"][idx, :int(h["align_len"][idx])].tobytes().decode("ascii")
+
+    def _load_series(self):
+        self.S, self.T = self._aligner.pairs[self.gene]
+
+    def _load_core(self):
+        al, idx, h = self._aligner, self._gene_idx, self._results()
+        nT = al.n_artificial_time_points
+        dp = orgalign.DP5(al, idx, self.S, self.T, self.alignment_str, np.float64(h["opt_cost"][idx]),
+                          al._aligned_state_params)
+        self.fwd_DP = dp
+        self.landscape_obj = orgalign.AlignmentLandscape(dp, h["l_states"][idx].reshape(nT + 1, nT + 1), nT, nT)
+
+    def _load_regions(self):
+        regions = orgalign.legacy_matched_regions(self.alignment_str)
+        self.match_regions_S, self.match_regions_T, self.non_match_regions_S, self.non_match_regions_T = regions
 
     # -- percentages (Main.py:103-127) ------------------------------------------------------------
     def compute_series_match_percentage(self):
         s = self.alignment_str
         n_m, n_v, n_w = s.count("M"), s.count("V"), s.count("W")
         self.match_percentage = round(((n_m + n_v + n_w) / len(s)) * 100, 2)
-        self.match_percentage_T = round(((n_m + n_v) / len(self.T.mean_trend)) * 100, 2)
-        self.match_percentage_S = round(((n_m + n_w) / len(self.S.mean_trend)) * 100, 2)
+        n_bins = self._aligner.n_artificial_time_points  # len(T.data_bins) == len(S.data_bins)
+        self.match_percentage_T = round(((n_m + n_v) / n_bins) * 100, 2)
+        self.match_percentage_S = round(((n_m + n_w) / n_bins) * 100, 2)
 
     def get_series_match_percentage(self):
         return self.match_percentage, self.match_percentage_S, self.match_percentage_T
 
     def get_opt_alignment_cost(self):
-        return self.fwd_DP.opt_cost
+        return np.float64(self._results()["opt_cost"][self._gene_idx])
 
     # -- lazily derived fields (reference computes them eagerly in run_DEAnalyser, Main.py:129-138) --
     def _ensure_visual(self):
@@ -417,6 +452,7 @@ class RefQueryAligner:
                 self._interp = True
             eng.run_dp()
             self._host = eng.results_to_host()
+        self._aligned_state_params = tuple(self.state_params)
         bad = np.nonzero(self._host["flags"] & _FLAG_BAD_SIGMA)[0]
         if len(bad):
             g = self.gene_list[int(bad[0])]
@@ -438,15 +474,7 @@ class RefQueryAligner:
         return [S, T]
 
     def _make_result(self, idx, host=None):
-        h = self._host if host is None else host
-        gene = self.gene_list[idx]
-        S, T = self.pairs[gene]
-        n = int(h["align_len"][idx])
-        s = h["align_str"][idx, :n].tobytes().decode("ascii")
-        nT = self.n_artificial_time_points
-        dp = orgalign.DP5(self, idx, S, T, s, np.float64(h["opt_cost"][idx]), self.state_params)
-        land = orgalign.AlignmentLandscape(dp, h["l_states"][idx].reshape(nT + 1, nT + 1), nT, nT)
-        return AligmentObj(self, idx, gene, S, T, dp, land)
+        return AligmentObj(self, idx, self.gene_list[idx], host)
 
     def _dense_dump(self, idx):
         """Dense DP matrices / back-pointers / cost terms of one gene (K4 in dump mode)."""
@@ -492,6 +520,7 @@ class RefQueryAligner:
             torch.cuda.current_stream().synchronize()
         one = {k: out[k].cpu().numpy() for k in ("align_str", "align_len", "opt_cost", "l_states")}
         view = {k: _Shift(one[k], gene_idx) for k in one}
+        self._aligned_state_params = tuple(self.state_params)
         return self._make_result(gene_idx, view)
 
     def align_all_pairs(self, concurrent=False, n_processes=None):

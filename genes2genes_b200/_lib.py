@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libg2g.so")
+# G2G_LIBRARY selects another build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("G2G_LIBRARY") or os.path.join(_HERE, "libg2g.so")
 
 c_i32, c_i64, c_f64, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
 
@@ -38,8 +39,9 @@ SIGNATURES = {
     "g2g_weights": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_pilot_mean": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "g2g_moments": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp]),
+    "g2g_fixup_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "g2g_fixup_trends": (c_i32, [ctypes.POINTER(Side), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32,
-                                 c_vp, c_vp, c_vp, c_vp, c_vp]),
+                                 c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_cost_dp": (c_i32, [c_vp, c_i64, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, c_i32,
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }

@@ -29,13 +29,14 @@ static inline int64_t g2g_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / 
 
 // Bin tiling shared by K0 (table layout) and K1 (register tile): see g2g_layout_t.
 struct G2GTiling {
-  int n_groups, bins_per_group, row_floats, genes_per_thread;
+  int n_groups, bins_per_group, bins_even, row_floats, genes_per_thread;
 };
 static inline G2GTiling g2g_tiling(int n_bins) {
   G2GTiling t;
   t.n_groups = (int)g2g_ceil_div(n_bins, 56);
   t.bins_per_group = (int)g2g_ceil_div(n_bins, t.n_groups);
-  t.row_floats = (int)g2g_round_up(t.bins_per_group + 2, 4);
-  t.genes_per_thread = t.bins_per_group <= 28 ? 2 : 1;
+  t.bins_even = (t.bins_per_group + 1) & ~1;  // K1 packs bins in pairs (FFMA2); odd counts get a zero bin
+  t.row_floats = (int)g2g_round_up(t.bins_even + 2, 4);
+  t.genes_per_thread = t.bins_even <= 28 ? 2 : 1;
   return t;
 }

@@ -35,47 +35,56 @@ struct Mask128 {
   __device__ bool any() const { return (lo | hi) != 0ull; }
 };
 
-__device__ double reduce_f64(const FixSide& s, long long q, long long g, long long g_stride, int T) {
-  double r = 0.0;
-  const size_t plane = (size_t)(2 * T + 1) * g_stride;
-  for (long long k = 0; k < s.n_split; ++k) r += s.part_f64[(size_t)k * plane + (size_t)q * g_stride + g];
-  return r;
-}
-__device__ int reduce_i32(const FixSide& s, long long q, long long g, long long g_stride, int T) {
-  int r = 0;
-  const size_t plane = (size_t)T * g_stride;
-  for (long long k = 0; k < s.n_split; ++k) r += s.part_i32[(size_t)k * plane + (size_t)q * g_stride + g];
-  return r;
+// Stage 1: sum the per-split partials of K1 in split order (fixed => deterministic), one thread per
+// (side, row, gene); coalesced over genes.
+struct ReduceParams {
+  const double* part_f64[2];
+  const int32_t* part_i32[2];
+  double* red_f64[2];
+  int32_t* red_i32[2];
+  long long n_split[2];
+  long long n_genes, g_stride;
+  int n_bins;
+};
+
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
+  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= p.n_genes) return;
+  const int T = p.n_bins;
+  const int rows_per_side = 3 * T + 1;
+  const int side = blockIdx.y / rows_per_side;
+  const int row = blockIdx.y % rows_per_side;
+  const long long ns = p.n_split[side];
+  if (row < 2 * T + 1) {
+    const size_t plane = (size_t)(2 * T + 1) * p.g_stride;
+    const double* src = p.part_f64[side] + (size_t)row * p.g_stride + g;
+    double r = 0.0;
+    for (long long k = 0; k < ns; ++k) r += src[(size_t)k * plane];
+    p.red_f64[side][(size_t)row * p.g_stride + g] = r;
+  } else {
+    const int q = row - (2 * T + 1);
+    const size_t plane = (size_t)T * p.g_stride;
+    const int32_t* src = p.part_i32[side] + (size_t)q * p.g_stride + g;
+    int r = 0;
+    for (long long k = 0; k < ns; ++k) r += src[(size_t)k * plane];
+    p.red_i32[side][(size_t)q * p.g_stride + g] = r;
+  }
 }
 
-// weighted mean / std of one bin (TimeSeriesPreprocessor.py:164-174), from the shifted sums:
-//   mean = a + sum w(x-a) / sum w
-//   sum w (x - xbar)^2 = sum w (x-a)^2 - 2 d sum w(x-a) + d^2 sum w,   d = xbar - a
-__device__ void bin_stat(const FixSide& s, long long g, long long g_stride, int T, int t, double a,
-                         double delta, double& mean, double& sd) {
-  const double sw = s.sum_w[t];
-  const double A = reduce_f64(s, t, g, g_stride, T);
-  const double Bq = reduce_f64(s, T + t, g, g_stride, T);
-  const double n = (double)s.n_cells;
-  mean = a + A / sw;
-  double wss = Bq - 2.0 * delta * A + delta * delta * sw;
-  if (wss < 0.0) wss = 0.0;
-  sd = sqrt(wss / (sw * (n - 1.0) / n)) * (sw / n);
-}
-
-// Main.py:293-304 + 261-291 on the per-window nnz counts; returns the mask of interpolation points
-// whose value appears in the significant-region list (np.in1d(points, regions), Main.py:356...).
-__device__ Mask128 region_mask(const FixSide& s, long long g, long long g_stride, int T, const double* pts) {
+// Main.py:293-304 + 261-291 on the window flags (bit k = window [p_k, p_{k+1}) has <= 3 non-zero
+// cells); returns the mask of interpolation points whose value appears in the significant-region
+// list (np.in1d(points, regions), Main.py:356...).
+__device__ Mask128 region_mask(const Mask128& flagged, int T, const double* pts) {
   Mask128 m = {0ull, 0ull};
   int last_flag = -1;
   for (int k = 0; k + 1 < T; ++k)
-    if (reduce_i32(s, k, g, g_stride, T) <= 3) last_flag = k;
+    if (flagged.get(k)) last_flag = k;
   if (last_flag < 0) return m;
   int run_start = -1;
   for (int k = 0; k + 1 < T; ++k) {
-    const bool f = reduce_i32(s, k, g, g_stride, T) <= 3;
+    const bool f = flagged.get(k);
     if (f && run_start < 0) run_start = k;
-    const bool next_f = (k + 2 < T) && (reduce_i32(s, k + 1, g, g_stride, T) <= 3);
+    const bool next_f = (k + 2 < T) && flagged.get(k + 1);
     if (f && !next_f) {  // run [run_start, k] ends here
       const bool is_last_run = (k == last_flag);
       const bool long_enough = (pts[k + 1] - pts[run_start]) > 0.2;
@@ -89,30 +98,66 @@ __device__ Mask128 region_mask(const FixSide& s, long long g, long long g_stride
   return m;
 }
 
-__global__ void __launch_bounds__(128) fixup_kernel(const FixParams p) {
-  const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+constexpr int kFixWarps = 4;
+constexpr int kMaxChunks = G2G_MAX_BINS / 32;
+
+// Stage 2: one warp per gene, lanes over interpolation points.
+__global__ void __launch_bounds__(kFixWarps * 32) fixup_kernel(const FixParams p) {
+  const long long g = (long long)blockIdx.x * kFixWarps + (threadIdx.x >> 5);
   if (g >= p.n_genes) return;
+  const int lane = threadIdx.x & 31;
   const int T = p.n_bins;
   const long long gs = p.g_stride;
-  double a[2], delta[2], min_sd[2];
+  const int n_chunks = (T + 31) / 32;
+  const double inf = __longlong_as_double(0x7ff0000000000000LL);
+
+  double mean[2][kMaxChunks], sd[2][kMaxChunks], min_sd[2];
   int nz[2];
+  Mask128 flagged[2];
+#pragma unroll
   for (int sd_i = 0; sd_i < 2; ++sd_i) {
     const FixSide& s = p.side[sd_i];
-    a[sd_i] = (double)s.pilot[g];
-    delta[sd_i] = reduce_f64(s, 2 * T, g, gs, T) / (double)s.n_cells;  // xbar - a
-    int c = 0;
-    for (int k = 0; k < T; ++k) c += reduce_i32(s, k, g, gs, T);
-    nz[sd_i] = c;
-    double mn = __longlong_as_double(0x7ff0000000000000LL);
-    for (int t = 0; t < T; ++t) {
-      double mean, sd;
-      bin_stat(s, g, gs, T, t, a[sd_i], delta[sd_i], mean, sd);
-      mn = sd < mn ? sd : mn;
+    const double a = (double)s.pilot[g];
+    const double n = (double)s.n_cells;
+    const double delta = s.part_f64[(size_t)(2 * T) * gs + g] / n;  // xbar - a
+    double mn = inf;
+    int cnt = 0;
+    flagged[sd_i].lo = flagged[sd_i].hi = 0ull;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      mean[sd_i][c] = 0.0;
+      sd[sd_i][c] = inf;
+      if (c < n_chunks) {
+        const int t = c * 32 + lane;
+        int cw = 0x7fffffff;
+        if (t < T) {
+          // weighted mean / std of one bin (TimeSeriesPreprocessor.py:164-174) from the single-pass
+          // sums A = sum w x, B = sum w (x-a)^2 (a = pilot shift), with d = xbar - a:
+          //   mean = A / sum w;   sum w (x - xbar)^2 = B - 2 d (A - a sum w) + d^2 sum w
+          const double sw = s.sum_w[t];
+          const double A = s.part_f64[(size_t)t * gs + g];
+          const double Bq = s.part_f64[(size_t)(T + t) * gs + g];
+          double wss = Bq - 2.0 * delta * (A - a * sw) + delta * delta * sw;
+          if (wss < 0.0) wss = 0.0;
+          mean[sd_i][c] = A / sw;
+          sd[sd_i][c] = sqrt(wss / (sw * (n - 1.0) / n)) * (sw / n);
+          cw = s.part_i32[(size_t)t * gs + g];
+          cnt += cw;
+        }
+        mn = fmin(mn, sd[sd_i][c]);
+        const unsigned bal = __ballot_sync(0xffffffffu, t + 1 < T && cw <= 3);
+        if (c < 2) flagged[sd_i].lo |= (unsigned long long)bal << (32 * c);
+        else flagged[sd_i].hi |= (unsigned long long)bal << (32 * (c - 2));
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+      cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     min_sd[sd_i] = mn;
+    nz[sd_i] = cnt;
   }
-  p.nnz[2 * g] = nz[0];
-  p.nnz[2 * g + 1] = nz[1];
 
   // policy (Main.py:344-406).  mode per side: 0 estimate, 1 estimate + region override, 2 all bins user-given
   int flags;
@@ -124,16 +169,16 @@ __global__ void __launch_bounds__(128) fixup_kernel(const FixParams p) {
     flags = 0; common = 0.01; mode[0] = 2; mode[1] = 2;
   } else if (zr) {
     flags = 1; common = min_sd[1] / 10.0; mode[0] = 2;
-    mask[1] = region_mask(p.side[1], g, gs, T, p.points);
+    mask[1] = region_mask(flagged[1], T, p.points);
     if (mask[1].any()) { mode[1] = 1; flags |= G2G_FLAG_REGION_QUERY; }
   } else if (zq) {
     flags = 2; common = min_sd[0] / 10.0; mode[1] = 2;
-    mask[0] = region_mask(p.side[0], g, gs, T, p.points);
+    mask[0] = region_mask(flagged[0], T, p.points);
     if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
   } else {
     flags = 3;
-    mask[0] = region_mask(p.side[0], g, gs, T, p.points);
-    mask[1] = region_mask(p.side[1], g, gs, T, p.points);
+    mask[0] = region_mask(flagged[0], T, p.points);
+    mask[1] = region_mask(flagged[1], T, p.points);
     if (mask[0].any() || mask[1].any()) {
       common = fmin(min_sd[0], min_sd[1]) / 10.0;
       if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
@@ -142,54 +187,85 @@ __global__ void __launch_bounds__(128) fixup_kernel(const FixParams p) {
   }
 
   bool bad = false;
+#pragma unroll
   for (int sd_i = 0; sd_i < 2; ++sd_i) {
-    const FixSide& s = p.side[sd_i];
     double* ms = p.musigma + ((size_t)g * 4 + 2 * sd_i) * T;
     double* tr = p.trends + ((size_t)g * 4 + 2 * sd_i) * T;
-    for (int t = 0; t < T; ++t) {
-      double mean, sd;
-      const bool user = mode[sd_i] == 2 || (mode[sd_i] == 1 && mask[sd_i].get(t));
-      if (user) { mean = 0.0; sd = common; }  // TSP.py:175-177
-      else bin_stat(s, g, gs, T, t, a[sd_i], delta[sd_i], mean, sd);
-      if (!(sd > 0.0) || isinf(sd)) bad = true;
-      ms[t] = mean;
-      ms[T + t] = sd;
-      tr[t] = mean + sd * p.eps_mean[t];   // np.mean(mu + sigma*eps_t)
-      tr[T + t] = sd * p.eps_std[t];       // np.std(mu + sigma*eps_t)
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int t = c * 32 + lane;
+      if (c < n_chunks && t < T) {
+        double m = mean[sd_i][c], s = sd[sd_i][c];
+        const bool user = mode[sd_i] == 2 || (mode[sd_i] == 1 && mask[sd_i].get(t));
+        if (user) { m = 0.0; s = common; }  // TSP.py:175-177
+        if (!(s > 0.0) || isinf(s)) bad = true;
+        ms[t] = m;
+        ms[T + t] = s;
+        tr[t] = m + s * p.eps_mean[t];   // np.mean(mu + sigma*eps_t)
+        tr[T + t] = s * p.eps_std[t];    // np.std(mu + sigma*eps_t)
+      }
     }
   }
-  if (bad) flags |= G2G_FLAG_BAD_SIGMA;
-  p.flags[g] = flags;
+  bad = __any_sync(0xffffffffu, bad);
+  if (lane == 0) {
+    p.nnz[2 * g] = nz[0];
+    p.nnz[2 * g + 1] = nz[1];
+    p.flags[g] = flags | (bad ? G2G_FLAG_BAD_SIGMA : 0);
+  }
 }
 
 }  // namespace
 
+extern "C" size_t g2g_fixup_workspace_bytes(int64_t g_stride, int32_t n_bins) {
+  return (size_t)2 * ((size_t)(2 * n_bins + 1) * g_stride * sizeof(double) + (size_t)n_bins * g_stride * sizeof(int32_t));
+}
+
 extern "C" int g2g_fixup_trends(const g2g_side_t* sides, const double* sum_w_ref, const double* sum_w_query,
                                 const double* points, const double* eps_mean, const double* eps_std,
                                 int64_t n_genes, int64_t g_stride, int32_t n_bins, double* musigma,
-                                double* trends, int32_t* nnz, int32_t* flags, void* stream) {
+                                double* trends, int32_t* nnz, int32_t* flags, void* workspace,
+                                size_t workspace_bytes, void* stream) {
   G2G_REQUIRE(sides && sum_w_ref && sum_w_query && points && eps_mean && eps_std, "null input pointer");
   G2G_REQUIRE(musigma && trends && nnz && flags, "null output pointer");
   G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
   G2G_REQUIRE(n_genes >= 0 && g_stride >= n_genes, "bad gene counts");
+  G2G_REQUIRE(workspace && workspace_bytes >= g2g_fixup_workspace_bytes(g_stride, n_bins), "workspace too small");
+  G2G_REQUIRE(((uintptr_t)workspace & 7) == 0, "workspace must be 8-byte aligned");
   if (n_genes == 0) return G2G_OK;
   FixParams p;
+  ReduceParams rp;
+  rp.n_genes = n_genes; rp.g_stride = g_stride; rp.n_bins = n_bins;
+  {
+    char* w = reinterpret_cast<char*>(workspace);
+    const size_t f = (size_t)(2 * n_bins + 1) * g_stride * sizeof(double);
+    const size_t i = (size_t)n_bins * g_stride * sizeof(int32_t);
+    rp.red_f64[0] = reinterpret_cast<double*>(w);
+    rp.red_f64[1] = reinterpret_cast<double*>(w + f);
+    rp.red_i32[0] = reinterpret_cast<int32_t*>(w + 2 * f);
+    rp.red_i32[1] = reinterpret_cast<int32_t*>(w + 2 * f + i);
+  }
   for (int s = 0; s < 2; ++s) {
     G2G_REQUIRE(sides[s].part_f64 && sides[s].part_i32 && sides[s].pilot && sides[s].n_cells >= 1, "bad side");
     g2g_layout_t lay;
     int rc = g2g_layout(sides[s].n_cells, n_bins, &lay);
     if (rc != G2G_OK) return rc;
-    p.side[s].part_f64 = sides[s].part_f64;
-    p.side[s].part_i32 = sides[s].part_i32;
+    rp.part_f64[s] = sides[s].part_f64;
+    rp.part_i32[s] = sides[s].part_i32;
+    rp.n_split[s] = lay.n_split;
+    p.side[s].part_f64 = rp.red_f64[s];
+    p.side[s].part_i32 = rp.red_i32[s];
     p.side[s].pilot = sides[s].pilot;
     p.side[s].sum_w = s == 0 ? sum_w_ref : sum_w_query;
     p.side[s].n_cells = sides[s].n_cells;
-    p.side[s].n_split = lay.n_split;
+    p.side[s].n_split = 1;
   }
   p.points = points; p.eps_mean = eps_mean; p.eps_std = eps_std;
   p.musigma = musigma; p.trends = trends; p.nnz = nnz; p.flags = flags;
   p.n_genes = n_genes; p.g_stride = g_stride; p.n_bins = n_bins;
-  fixup_kernel<<<(unsigned)g2g_ceil_div(n_genes, 128), 128, 0, (cudaStream_t)stream>>>(p);
+  dim3 rgrid((unsigned)g2g_ceil_div(n_genes, 256), (unsigned)(2 * (3 * n_bins + 1)));
+  reduce_partials_kernel<<<rgrid, 256, 0, (cudaStream_t)stream>>>(rp);
+  G2G_CUDA_TRY(cudaGetLastError());
+  fixup_kernel<<<(unsigned)g2g_ceil_div(n_genes, kFixWarps), kFixWarps * 32, 0, (cudaStream_t)stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
 }

@@ -1,6 +1,6 @@
 // K1  g2g_moments: single pass over the expression matrix (cells x genes, f32) of up to two
 // datasets, producing per (gene, bin) the shifted weighted moments
-//     A = sum_c w[t,c] (x_c - a),   B = sum_c w[t,c] (x_c - a)^2,   C = sum_c (x_c - a)
+//     A = sum_c w[t,c] x_c,   B = sum_c w[t,c] (x_c - a)^2,   C = sum_c (x_c - a)
 // and the non-zero counts per pseudotime window.  Replaces the per-gene pandas/numpy loop of
 // TimeSeriesPreprocessor.compute_stat (TSP.py:161-174) and the counts of Main.py:298-301,344-363.
 //
@@ -10,9 +10,10 @@
 // mbarriers; the warp that finishes a stage last re-arms it with the next tile, so there is no
 // producer warp and no blocking hand-off.  Eight warps each take 8 cells of a stage; every thread owns GX
 // genes x TB bins x {A,B} float accumulators in registers (an FFMA register tile: the weights are
-// warp-broadcast LDS.128, X is a conflict-free LDS).  Every kFlushStages stages the f32 partials
-// are added into CTA-wide f64 accumulators in shared memory, warp after warp in a fixed order, so
-// results do not depend on scheduling; the item's f64 sums go to its own slot of `part_f64`.
+// warp-broadcast LDS.128, X is a conflict-free LDS; two bins are packed per FFMA2).  Every
+// kFlushStages stages, and at the end of an item, the eight warps' f32 partials are summed in f64 in
+// a fixed order through a shared staging area, so results do not depend on scheduling; the item's
+// f64 sums go to its own slot of `part_f64`.
 #include "g2g_common.cuh"
 #include <cuda.h>
 
@@ -22,7 +23,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kCellTile = G2G_CELL_TILE;              // rows per stage
 constexpr int kCellsPerWarp = kCellTile / kConsumerWarps;
-constexpr int kFlushStages = 8;                        // f32 run length per thread = 8 stages * 8 cells = 64 cells
+constexpr int kFlushStages = 16;                       // f32 run length per thread = 16 stages * 8 cells = 128 cells
 constexpr int kMaxSides = 2;
 
 struct MomSide {
@@ -40,16 +41,13 @@ struct MomParams {
   CUtensorMap tmap[kMaxSides];
   MomSide side[kMaxSides];
   long long n_genes, g_stride;
-  int n_sides, n_bins, n_groups, n_gtiles, n_items, n_stages;
+  int n_sides, n_bins, n_groups, bins_per_group, n_gtiles, n_items, n_stages;
 };
 
 // ---- raw PTX helpers (mbarrier + TMA) ----------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -79,16 +77,24 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void consumer_bar_sync() { __syncthreads(); }
+#ifndef G2G_MOM_MIN_BLOCKS
+#define G2G_MOM_MIN_BLOCKS 1   // CTAs per SM the register / shared-memory budget is sized for (tuning knob)
+#endif
 
-template <int TB, int GX>
+template <int TBE, int GX>
 struct Cfg {
+  static constexpr int NP = TBE / 2;                                  // packed bin pairs per thread
   static constexpr int GT = 32 * GX;                                  // genes per CTA tile
-  static constexpr int RF = (TB + 2 + 3) / 4 * 4;                     // floats per weight-table row
-  static constexpr int NQ = 2 * TB + 1;                               // f64 accumulator rows (A, B, C)
+  static constexpr int RF = (TBE + 2 + 3) / 4 * 4;                    // floats per weight-table row
+  static constexpr int NQ = 2 * TBE + 1;                              // accumulator rows (A bins, B bins, C)
   static constexpr int XBYTES = kCellTile * GT * 4;
   static constexpr int WBYTES = kCellTile * RF * 4;
   static constexpr int STAGE_BYTES = XBYTES + WBYTES;
+  // the cross-warp reduction goes through a shared staging area, in kPasses slices of kRows rows
+  static constexpr int kStagingCap = (G2G_MOM_MIN_BLOCKS >= 2 ? 16 : 64) * 1024;
+  static constexpr int kPasses = (kConsumerWarps * NQ * GT * 4 + kStagingCap - 1) / kStagingCap;
+  static constexpr int kRows = (NQ + kPasses - 1) / kPasses;
+  static constexpr int STAGING_BYTES = kConsumerWarps * kRows * GT * 4;
 };
 
 struct Item {
@@ -112,40 +118,45 @@ __device__ __forceinline__ Item decode_item(const MomParams& p, int item) {
   return it;
 }
 
-#ifndef G2G_MOM_MIN_BLOCKS
-#define G2G_MOM_MIN_BLOCKS 1   // CTAs per SM the register budget is sized for (tuning knob)
-#endif
-template <int TB, int GX>
+// acc{lo,hi} += w2{lo,hi} * x   -- one packed FFMA2 (two bins of one gene); the scalar x is a
+// broadcast operand in SASS (FFMA2 Rd, Ra.F32x2.HI_LO, Rb.F32, Rc.F32x2.HI_LO)
+__device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned long long w2, float x) {
+  asm("{\n.reg .b64 xx;\nmov.b64 xx, {%2, %2};\nfma.rn.f32x2 %0, %1, xx, %0;\n}" : "+l"(acc) : "l"(w2), "f"(x));
+}
+__device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+
+template <int TBE, int GX>
 __global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(const __grid_constant__ MomParams p) {
-  using C = Cfg<TB, GX>;
-  constexpr int kCellUnroll = (2 * TB * GX <= 64) ? 2 : 1;
+  using C = Cfg<TBE, GX>;
+  constexpr int NP = C::NP;
+  constexpr int kCellUnroll = (2 * TBE * GX <= 64) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_stages = p.n_stages;
-  // layout: [stages][X tile | W slice] | acc64 [NQ][GT] | cnt [n_bins][GT] | barriers
+  // layout: [stages][X tile | W slice] | staging | acc64 [NQ][GT] | cnt [n_bins][GT] | barriers, counters
   unsigned char* stage_base = smem;
-  double* acc64 = reinterpret_cast<double*>(smem + (size_t)n_stages * C::STAGE_BYTES);
+  float* staging = reinterpret_cast<float*>(smem + (size_t)n_stages * C::STAGE_BYTES);
+  double* acc64 = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(staging) + C::STAGING_BYTES);
   int* cnt_s = reinterpret_cast<int*>(acc64 + C::NQ * C::GT);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(cnt_s + (size_t)p.n_bins * C::GT);
-  uint64_t* flush_bar = full_bar + n_stages;
-  int* done = reinterpret_cast<int*>(flush_bar + kConsumerWarps);  // warps finished with each stage
-  int* cursor = done + n_stages;                                    // {next item, next tile} to load
+  int* done = reinterpret_cast<int*>(full_bar + n_stages);  // warps finished with each stage
+  int* cursor = done + n_stages;                             // {next item, next tile} to load
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tid = threadIdx.x;
 
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) {
       mbar_init(&full_bar[s], 1);
       done[s] = 0;
     }
     cursor[0] = blockIdx.x;
     cursor[1] = 0;
-    for (int w = 0; w < kConsumerWarps; ++w) mbar_init(&flush_bar[w], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int k = threadIdx.x; k < C::NQ * C::GT; k += kThreads) acc64[k] = 0.0;
-  for (int k = threadIdx.x; k < p.n_bins * C::GT; k += kThreads) cnt_s[k] = 0;
+  for (int k = tid; k < C::NQ * C::GT; k += kThreads) acc64[k] = 0.0;
+  for (int k = tid; k < p.n_bins * C::GT; k += kThreads) cnt_s[k] = 0;
   __syncthreads();
-  if (threadIdx.x == 0) mbar_arrive(&flush_bar[0]);  // warp 0 may flush first
 
   // Load the next tile of this CTA's item sequence into `slot`.  Only one thread runs this at a
   // time: the prologue, then whichever warp finished the previous occupant of the slot last.
@@ -164,48 +175,83 @@ __global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(c
     if (tile + 1 == it.n_tiles) { cursor[0] = item + gridDim.x; cursor[1] = 0; }
     else cursor[1] = tile + 1;
   };
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     for (int s = 0; s < n_stages; ++s) issue_next(s);
     __threadfence_block();
   }
   __syncthreads();
 
-  // ================= consumers ====================================================================
-  float accA[GX][TB], accB[GX][TB], accC[GX];
+  // ---- register tile: GX genes x TBE bins x {A, B} as packed f32 pairs, plus C per gene ----------
+  unsigned long long accA[GX][NP], accB[GX][NP];
+  float accC[GX];
   int cnt[GX];
 #pragma unroll
   for (int x = 0; x < GX; ++x) {
     accC[x] = 0.0f;
     cnt[x] = 0;
 #pragma unroll
-    for (int t = 0; t < TB; ++t) { accA[x][t] = 0.0f; accB[x][t] = 0.0f; }
+    for (int k = 0; k < NP; ++k) { accA[x][k] = 0ull; accB[x][k] = 0ull; }
   }
   int slot = 0;
-  uint32_t phase = 0, flush_phase = 0;
+  uint32_t phase = 0;
 
-  // ordered f32 -> f64 flush: warp w adds after warp w-1 (token passed through flush_bar)
-  auto flush = [&]() {
-    mbar_wait(&flush_bar[warp], flush_phase);
-    flush_phase ^= 1;
+  // f32 -> f64 reduction across the eight warps (all threads of the CTA take part).  Every warp
+  // stores its partial sums to the staging area; thread k then adds the eight values of slot k in
+  // warp order to the CTA's f64 accumulator -- a fixed summation order.  `final` also adds the f64
+  // accumulator, writes the item's result to global memory and clears it.
+  auto reduce_flush = [&](bool final, const Item& it) {
+    const MomSide& s = p.side[it.side];
+    const int T = p.n_bins, TB = p.bins_per_group;
+    const long long g0 = (long long)it.gt * C::GT;
+    double* pf = s.part_f64 + (size_t)it.split * (2 * T + 1) * p.g_stride;
 #pragma unroll
-    for (int t = 0; t < TB; ++t) {
+    for (int pass = 0; pass < C::kPasses; ++pass) {
+      const int r0 = pass * C::kRows;
+      float* mine = staging + (size_t)warp * C::kRows * C::GT + lane * GX;
 #pragma unroll
-      for (int x = 0; x < GX; ++x) {
-        double* a = acc64 + (size_t)t * C::GT + lane * GX + x;
-        double* b = acc64 + (size_t)(TB + t) * C::GT + lane * GX + x;
-        *a += (double)accA[x][t];
-        *b += (double)accB[x][t];
-        accA[x][t] = 0.0f;
-        accB[x][t] = 0.0f;
+      for (int k = 0; k < NP; ++k) {
+#pragma unroll
+        for (int x = 0; x < GX; ++x) {
+          const int qa = 2 * k, qb = TBE + 2 * k;
+          if (qa >= r0 && qa < r0 + C::kRows) mine[(qa - r0) * C::GT + x] = lo_f(accA[x][k]);
+          if (qa + 1 >= r0 && qa + 1 < r0 + C::kRows) mine[(qa + 1 - r0) * C::GT + x] = hi_f(accA[x][k]);
+          if (qb >= r0 && qb < r0 + C::kRows) mine[(qb - r0) * C::GT + x] = lo_f(accB[x][k]);
+          if (qb + 1 >= r0 && qb + 1 < r0 + C::kRows) mine[(qb + 1 - r0) * C::GT + x] = hi_f(accB[x][k]);
+        }
       }
+      if (2 * TBE >= r0 && 2 * TBE < r0 + C::kRows) {
+#pragma unroll
+        for (int x = 0; x < GX; ++x) mine[(2 * TBE - r0) * C::GT + x] = accC[x];
+      }
+      __syncthreads();
+      const int n_slots = ((C::NQ - r0 < C::kRows) ? (C::NQ - r0) : C::kRows) * C::GT;
+      for (int k = tid; k < n_slots; k += kThreads) {
+        double sum = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) sum += (double)staging[(size_t)w * C::kRows * C::GT + k];
+        const int slot64 = r0 * C::GT + k;
+        sum += acc64[slot64];
+        if (final) {
+          const int q = slot64 / C::GT, gl = slot64 % C::GT;
+          const long long g = g0 + gl;
+          int row = -1;
+          if (q < TBE) { int t = it.bg * TB + q; if (q < TB && t < T) row = t; }
+          else if (q < 2 * TBE) { int t = it.bg * TB + (q - TBE); if (q - TBE < TB && t < T) row = T + t; }
+          else if (it.bg == 0) row = 2 * T;
+          if (row >= 0 && g < p.n_genes) pf[(size_t)row * p.g_stride + g] = sum;
+          acc64[slot64] = 0.0;
+        } else {
+          acc64[slot64] = sum;
+        }
+      }
+      __syncthreads();
     }
 #pragma unroll
     for (int x = 0; x < GX; ++x) {
-      acc64[(size_t)(2 * TB) * C::GT + lane * GX + x] += (double)accC[x];
       accC[x] = 0.0f;
+#pragma unroll
+      for (int k = 0; k < NP; ++k) { accA[x][k] = 0ull; accB[x][k] = 0ull; }
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&flush_bar[(warp + 1) % kConsumerWarps]);
   };
 
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -218,21 +264,39 @@ __global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(c
       long long g = (long long)it.gt * C::GT + lane * GX + x;
       a[x] = g < p.n_genes ? s.pilot[g] : 0.0f;
     }
-    int cur_win = -1;
+    int cur_win = -1;     // window the running counts `cnt` belong to
     int since_flush = 0;
+    auto flush_counts = [&]() {
+      if (do_counts && cur_win >= 0) {
+#pragma unroll
+        for (int x = 0; x < GX; ++x)
+          if (cnt[x]) atomicAdd(&cnt_s[cur_win * C::GT + lane * GX + x], cnt[x]);
+      }
+#pragma unroll
+      for (int x = 0; x < GX; ++x) cnt[x] = 0;
+    };
     for (int tile = 0; tile < it.n_tiles; ++tile) {
       mbar_wait(&full_bar[slot], phase);
       const float* xt = reinterpret_cast<const float*>(stage_base + (size_t)slot * C::STAGE_BYTES);
       const float* wt = xt + kCellTile * C::GT;
+      const int cell0 = warp * kCellsPerWarp;
+      // counts: branch-free while all of this warp's cells share one window (time-sorted input),
+      // per-cell bookkeeping otherwise
+      int tile_cnt[GX];
+#pragma unroll
+      for (int x = 0; x < GX; ++x) tile_cnt[x] = 0;
+      const int win0 = __float_as_int(wt[cell0 * C::RF + TBE + 1]);
+      int win_diff = 0;
 #pragma unroll(kCellUnroll)
       for (int cc = 0; cc < kCellsPerWarp; ++cc) {
-        const int cell = warp * kCellsPerWarp + cc;
-        float w[C::RF];
-        const float4* wrow = reinterpret_cast<const float4*>(wt + cell * C::RF);
+        const int cell = cell0 + cc;
+        const ulonglong2* wrow = reinterpret_cast<const ulonglong2*>(wt + cell * C::RF);
+        unsigned long long w2[C::RF / 2];
 #pragma unroll
         for (int q = 0; q < C::RF / 4; ++q) {
-          float4 v = wrow[q];
-          w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+          ulonglong2 v = wrow[q];
+          w2[2 * q] = v.x;
+          w2[2 * q + 1] = v.y;
         }
         float xv[GX];
         if constexpr (GX == 2) {
@@ -241,28 +305,34 @@ __global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(c
         } else {
           xv[0] = xt[cell * C::GT + lane];
         }
-        const int win = __float_as_int(w[TB + 1]);
-        if (win != cur_win) {  // warp-uniform: every lane looks at the same cell
-          if (do_counts && cur_win >= 0) {
-#pragma unroll
-            for (int x = 0; x < GX; ++x)
-              if (cnt[x]) atomicAdd(&cnt_s[cur_win * C::GT + lane * GX + x], cnt[x]);
-          }
-#pragma unroll
-          for (int x = 0; x < GX; ++x) cnt[x] = 0;
-          cur_win = win;
-        }
+        const float valid = lo_f(w2[NP]);
+        win_diff |= __float_as_int(hi_f(w2[NP])) ^ win0;
 #pragma unroll
         for (int x = 0; x < GX; ++x) {
           const float d = xv[x] - a[x];
           const float y = d * d;
 #pragma unroll
-          for (int t = 0; t < TB; ++t) {
-            accA[x][t] = fmaf(w[t], d, accA[x][t]);
-            accB[x][t] = fmaf(w[t], y, accB[x][t]);
+          for (int k = 0; k < NP; ++k) {
+            ffma2_bcast(accA[x][k], w2[k], xv[x]);
+            ffma2_bcast(accB[x][k], w2[k], y);
           }
-          accC[x] = fmaf(w[TB], d, accC[x]);
-          cnt[x] += (xv[x] != 0.0f) ? 1 : 0;
+          accC[x] = fmaf(valid, d, accC[x]);
+          tile_cnt[x] += (xv[x] != 0.0f) ? 1 : 0;
+        }
+      }
+      if (do_counts) {
+        if (win_diff == 0) {  // warp-uniform
+          if (win0 != cur_win) { flush_counts(); cur_win = win0; }
+#pragma unroll
+          for (int x = 0; x < GX; ++x) cnt[x] += tile_cnt[x];
+        } else {
+          for (int cc = 0; cc < kCellsPerWarp; ++cc) {
+            const int cell = cell0 + cc;
+            const int win = __float_as_int(wt[cell * C::RF + TBE + 1]);
+            if (win != cur_win) { flush_counts(); cur_win = win; }
+#pragma unroll
+            for (int x = 0; x < GX; ++x) cnt[x] += (xt[cell * C::GT + lane * GX + x] != 0.0f) ? 1 : 0;
+          }
         }
       }
       __syncwarp();
@@ -276,44 +346,22 @@ __global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(c
         }
       }
       if (++slot == n_stages) { slot = 0; phase ^= 1; }
-      if (++since_flush == kFlushStages) { flush(); since_flush = 0; }
+      if (++since_flush == kFlushStages && tile + 1 < it.n_tiles) { reduce_flush(false, it); since_flush = 0; }
     }
-    flush();  // every warp flushes exactly once more per item, keeping the token ring in step
-    if (do_counts && cur_win >= 0) {
-#pragma unroll
-      for (int x = 0; x < GX; ++x)
-        if (cnt[x]) atomicAdd(&cnt_s[cur_win * C::GT + lane * GX + x], cnt[x]);
-    }
-#pragma unroll
-    for (int x = 0; x < GX; ++x) cnt[x] = 0;
-    consumer_bar_sync();
-    // write this item's sums to its slot of the partial buffers and clear the accumulators
-    {
-      const int tid = threadIdx.x;
+    flush_counts();
+    reduce_flush(true, it);   // its barriers also order the count atomics before the write-out below
+    if (do_counts) {
       const int T = p.n_bins;
       const long long g0 = (long long)it.gt * C::GT;
-      double* pf = s.part_f64 + (size_t)it.split * (2 * T + 1) * p.g_stride;
-      for (int k = tid; k < C::NQ * C::GT; k += kConsumerWarps * 32) {
+      int32_t* pi = s.part_i32 + (size_t)it.split * T * p.g_stride;
+      for (int k = tid; k < T * C::GT; k += kThreads) {
         const int q = k / C::GT, gl = k % C::GT;
         const long long g = g0 + gl;
-        int row = -1;
-        if (q < TB) { int t = it.bg * TB + q; if (t < T) row = t; }
-        else if (q < 2 * TB) { int t = it.bg * TB + (q - TB); if (t < T) row = T + t; }
-        else if (do_counts) row = 2 * T;
-        if (row >= 0 && g < p.n_genes) pf[(size_t)row * p.g_stride + g] = acc64[k];
-        acc64[k] = 0.0;
+        if (g < p.n_genes) pi[(size_t)q * p.g_stride + g] = cnt_s[k];
+        cnt_s[k] = 0;
       }
-      if (do_counts) {
-        int32_t* pi = s.part_i32 + (size_t)it.split * T * p.g_stride;
-        for (int k = tid; k < T * C::GT; k += kConsumerWarps * 32) {
-          const int q = k / C::GT, gl = k % C::GT;
-          const long long g = g0 + gl;
-          if (g < p.n_genes) pi[(size_t)q * p.g_stride + g] = cnt_s[k];
-          cnt_s[k] = 0;
-        }
-      }
+      __syncthreads();
     }
-    consumer_bar_sync();
   }
 }
 
@@ -337,9 +385,9 @@ int get_encode_fn(EncodeTiledFn* out) {
   return G2G_OK;
 }
 
-template <int TB, int GX>
+template <int TBE, int GX>
 int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
-  using C = Cfg<TB, GX>;
+  using C = Cfg<TBE, GX>;
   EncodeTiledFn encode;
   int rc = get_encode_fn(&encode);
   if (rc != G2G_OK) return rc;
@@ -367,23 +415,24 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
   int dev = 0, n_sm = 0;
   G2G_CUDA_TRY(cudaGetDevice(&dev));
   G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
-  const size_t fixed = (size_t)C::NQ * C::GT * 8 + (size_t)p.n_bins * C::GT * 4 + (8 + kConsumerWarps) * 8 + (8 + 2) * 4 + 128;
+  const size_t fixed = (size_t)C::STAGING_BYTES + (size_t)C::NQ * C::GT * 8 + (size_t)p.n_bins * C::GT * 4 +
+                       8 * 8 + (8 + 2) * 4 + 128;
   // as many stages (<= 8, >= 2) as fit the shared memory of G2G_MOM_MIN_BLOCKS CTAs per SM
   int stages = 8;
   const size_t budget = (size_t)(G2G_MOM_MIN_BLOCKS >= 2 ? 110 : 200) * 1024;
   while (stages > 2 && fixed + (size_t)stages * C::STAGE_BYTES > budget) --stages;
   p.n_stages = stages;
   const size_t smem = fixed + (size_t)stages * C::STAGE_BYTES;
-  G2G_CUDA_TRY(cudaFuncSetAttribute(moments_kernel<TB, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  G2G_CUDA_TRY(cudaFuncSetAttribute(moments_kernel<TBE, GX>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int occ = 0;
-  G2G_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, moments_kernel<TB, GX>, kThreads, smem));
+  G2G_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, moments_kernel<TBE, GX>, kThreads, smem));
   if (occ < 1) {
     g2g_set_error("moments kernel does not fit on an SM (smem %zu bytes)", smem);
     return G2G_ERR_UNSUPPORTED;
   }
   int grid = n_sm * occ;
   if (grid > items) grid = items;
-  moments_kernel<TB, GX><<<grid, kThreads, smem, stream>>>(p);
+  moments_kernel<TBE, GX><<<grid, kThreads, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
 }
@@ -391,18 +440,14 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
 #define G2G_CASE2(TBV) case TBV: return launch_moments<TBV, 2>(p, sides, stream);
 #define G2G_CASE1(TBV) case TBV: return launch_moments<TBV, 1>(p, sides, stream);
 
-int dispatch_moments(MomParams& p, const g2g_side_t* sides, int bins_per_group, cudaStream_t stream) {
-  switch (bins_per_group) {
-    G2G_CASE2(1) G2G_CASE2(2) G2G_CASE2(3) G2G_CASE2(4) G2G_CASE2(5) G2G_CASE2(6) G2G_CASE2(7)
-    G2G_CASE2(8) G2G_CASE2(9) G2G_CASE2(10) G2G_CASE2(11) G2G_CASE2(12) G2G_CASE2(13) G2G_CASE2(14)
-    G2G_CASE2(15) G2G_CASE2(16) G2G_CASE2(17) G2G_CASE2(18) G2G_CASE2(19) G2G_CASE2(20) G2G_CASE2(21)
-    G2G_CASE2(22) G2G_CASE2(23) G2G_CASE2(24) G2G_CASE2(25) G2G_CASE2(26) G2G_CASE2(27) G2G_CASE2(28)
-    G2G_CASE1(29) G2G_CASE1(30) G2G_CASE1(31) G2G_CASE1(32) G2G_CASE1(33) G2G_CASE1(34) G2G_CASE1(35)
-    G2G_CASE1(36) G2G_CASE1(37) G2G_CASE1(38) G2G_CASE1(39) G2G_CASE1(40) G2G_CASE1(41) G2G_CASE1(42)
-    G2G_CASE1(43) G2G_CASE1(44) G2G_CASE1(45) G2G_CASE1(46) G2G_CASE1(47) G2G_CASE1(48) G2G_CASE1(49)
-    G2G_CASE1(50) G2G_CASE1(51) G2G_CASE1(52) G2G_CASE1(53) G2G_CASE1(54) G2G_CASE1(55) G2G_CASE1(56)
+int dispatch_moments(MomParams& p, const g2g_side_t* sides, int bins_even, cudaStream_t stream) {
+  switch (bins_even) {
+    G2G_CASE2(2) G2G_CASE2(4) G2G_CASE2(6) G2G_CASE2(8) G2G_CASE2(10) G2G_CASE2(12) G2G_CASE2(14)
+    G2G_CASE2(16) G2G_CASE2(18) G2G_CASE2(20) G2G_CASE2(22) G2G_CASE2(24) G2G_CASE2(26) G2G_CASE2(28)
+    G2G_CASE1(30) G2G_CASE1(32) G2G_CASE1(34) G2G_CASE1(36) G2G_CASE1(38) G2G_CASE1(40) G2G_CASE1(42)
+    G2G_CASE1(44) G2G_CASE1(46) G2G_CASE1(48) G2G_CASE1(50) G2G_CASE1(52) G2G_CASE1(54) G2G_CASE1(56)
     default:
-      g2g_set_error("bins_per_group %d has no compiled kernel", bins_per_group);
+      g2g_set_error("bins_even %d has no compiled kernel", bins_even);
       return G2G_ERR_UNSUPPORTED;
   }
 }
@@ -418,6 +463,7 @@ extern "C" int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_g
   G2GTiling t = g2g_tiling(n_bins);
   MomParams p;
   p.n_genes = n_genes; p.g_stride = g_stride; p.n_sides = n_sides; p.n_bins = n_bins; p.n_groups = t.n_groups;
+  p.bins_per_group = t.bins_per_group;
   for (int s = 0; s < n_sides; ++s) {
     const g2g_side_t& in = sides[s];
     G2G_REQUIRE(in.X && in.wtab && in.pilot && in.part_f64 && in.part_i32, "null pointer in side");
@@ -433,5 +479,5 @@ extern "C" int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_g
     p.side[s].n_pad = lay.n_pad; p.side[s].cells_per_item = lay.cells_per_item;
     p.side[s].n_split = (int)lay.n_split;
   }
-  return dispatch_moments(p, sides, t.bins_per_group, (cudaStream_t)stream);
+  return dispatch_moments(p, sides, t.bins_even, (cudaStream_t)stream);
 }

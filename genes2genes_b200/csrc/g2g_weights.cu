@@ -16,15 +16,22 @@ struct WeightsParams {
   double* partial;        // [n_blocks][T]
   unsigned int* counter;  // zeroed by the launcher
   long long n_cells, n_pad;
-  int n_bins, n_groups, bins_per_group, row_floats;
+  int n_bins, n_groups, bins_per_group, bins_even, row_floats;
 };
 
-// One thread per (padded) cell.  W[t,c] = exp(-(|tau_c - p_t|)^2 / denom_t) in float64
-// (TimeSeriesPreprocessor.py:48, 125-127), rounded once to float32 for the table.
+constexpr int kWCells = 64;                 // cells per block
+constexpr int kWLanes = kWThreads / kWCells;  // threads per cell, striding over the bins
+
+// W[t,c] = exp(-(|tau_c - p_t|)^2 / denom_t) in float64 (TimeSeriesPreprocessor.py:48, 125-127),
+// rounded once to float32 for the table.  Block = 64 cells x 4 bin lanes.  The per-bin sums of the
+// f64 weights are reduced in a fixed order: 16-cell partial sums, then 4 partials per block, then
+// (last block to finish) the blocks in index order.
 __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams p) {
   __shared__ double s_pts[G2G_MAX_BINS];
   __shared__ double s_den[G2G_MAX_BINS];
-  __shared__ double s_red[kWThreads / 32][G2G_MAX_BINS];
+  extern __shared__ double s_dyn[];                     // [T][kWCells + 1] weights, then [T][4] partial sums
+  double (*s_w)[kWCells + 1] = reinterpret_cast<double (*)[kWCells + 1]>(s_dyn);
+  double (*s_part)[4] = reinterpret_cast<double (*)[4]>(s_dyn + (size_t)p.n_bins * (kWCells + 1));
   __shared__ bool s_last;
   const int T = p.n_bins;
   for (int t = threadIdx.x; t < T; t += kWThreads) {
@@ -32,50 +39,55 @@ __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams 
     s_den[t] = p.denom[t];
   }
   __syncthreads();
-  const long long c = (long long)blockIdx.x * kWThreads + threadIdx.x;
+  const int cl = threadIdx.x % kWCells, bl = threadIdx.x / kWCells;
+  const long long c = (long long)blockIdx.x * kWCells + cl;
   const bool in_pad = c < p.n_pad;
   const bool valid = c < p.n_cells;
   const double tau = valid ? p.tau[c] : 0.0;
-  // window k: p_k <= tau < p_{k+1}  (half open, Main.py:299); cells outside every window -> T-1
-  int win = T - 1;
-  if (valid) {
-    for (int k = 0; k + 1 < T; ++k)
-      if (tau >= s_pts[k] && tau < s_pts[k + 1]) win = k;
-  }
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int g = 0; g < p.n_groups; ++g) {
-    float* row = p.wtab + ((size_t)g * p.n_pad + (size_t)c) * p.row_floats;
-    for (int b = 0; b < p.row_floats; ++b) {
-      const int t = g * p.bins_per_group + b;
-      float out = 0.0f;
-      double w = 0.0;
-      if (b < p.bins_per_group) {
-        if (valid && t < T) {
-          double d = fabs(tau - s_pts[t]);
-          w = exp(-((d * d) / s_den[t]));
-          out = (float)w;
-        }
-        if (t < T) {
-          // deterministic block reduction of the f64 weights: shuffle tree, then fixed warp order
-          double r = w;
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) r += __shfl_down_sync(0xffffffffu, r, o);
-          if (lane == 0) s_red[warp][t] = r;
-        }
-      } else if (b == p.bins_per_group) {
-        out = valid ? 1.0f : 0.0f;
-      } else if (b == p.bins_per_group + 1) {
-        out = __int_as_float(valid ? win : -1);
-      }
-      if (in_pad) row[b] = out;
+  for (int t = bl; t < T; t += kWLanes) {
+    double w = 0.0;
+    if (valid) {
+      double d = fabs(tau - s_pts[t]);
+      w = exp(-((d * d) / s_den[t]));
     }
+    s_w[t][cl] = w;
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < T; t += kWThreads) {
-    double r = 0.0;
-    for (int w = 0; w < kWThreads / 32; ++w) r += s_red[w][t];
-    p.partial[(size_t)blockIdx.x * T + t] = r;
+  // table rows: [w_0 .. w_{TB-1}, (zero bin when TB is odd), valid, window id, 0 pad] per group
+  if (in_pad) {
+    for (int g = 0; g < p.n_groups; ++g) {
+      float* row = p.wtab + ((size_t)g * p.n_pad + (size_t)c) * p.row_floats;
+      for (int b = bl; b < p.row_floats; b += kWLanes) {
+        const int t = g * p.bins_per_group + b;
+        float out = 0.0f;
+        if (b < p.bins_per_group) {
+          if (t < T) out = (float)s_w[t][cl];
+        } else if (b == p.bins_even) {
+          out = valid ? 1.0f : 0.0f;
+        } else if (b == p.bins_even + 1) {
+          // window k: p_k <= tau < p_{k+1}  (half open, Main.py:299); cells outside every window -> T-1
+          int win = -1;
+          if (valid) {
+            win = T - 1;
+            for (int k = 0; k + 1 < T; ++k)
+              if (tau >= s_pts[k] && tau < s_pts[k + 1]) win = k;
+          }
+          out = __int_as_float(win);
+        }
+        row[b] = out;
+      }
+    }
   }
+  for (int k = threadIdx.x; k < T * 4; k += kWThreads) {
+    const int t = k >> 2, q = k & 3;
+    double r = 0.0;
+#pragma unroll
+    for (int i = 0; i < kWCells / 4; ++i) r += s_w[t][q * (kWCells / 4) + i];
+    s_part[t][q] = r;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < T; t += kWThreads)
+    p.partial[(size_t)blockIdx.x * T + t] = ((s_part[t][0] + s_part[t][1]) + s_part[t][2]) + s_part[t][3];
   __threadfence();
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -143,7 +155,7 @@ extern "C" int g2g_layout(int64_t n_cells, int32_t n_bins, g2g_layout_t* out) {
 
 extern "C" size_t g2g_weights_workspace_bytes(int64_t n_cells, int32_t n_bins) {
   int64_t n_pad = g2g_round_up(n_cells, G2G_CELL_TILE);
-  int64_t blocks = g2g_ceil_div(n_pad, kWThreads);
+  int64_t blocks = g2g_ceil_div(n_pad, 64);
   return (size_t)blocks * n_bins * sizeof(double) + 16;
 }
 
@@ -159,13 +171,17 @@ extern "C" int g2g_weights(const double* tau, int64_t n_cells, const double* poi
   WeightsParams p;
   p.tau = tau; p.points = points; p.denom = denom; p.wtab = wtab; p.sum_w = sum_w;
   p.n_cells = n_cells; p.n_pad = g2g_round_up(n_cells, G2G_CELL_TILE);
-  p.n_bins = n_bins; p.n_groups = t.n_groups; p.bins_per_group = t.bins_per_group; p.row_floats = t.row_floats;
-  int64_t blocks = g2g_ceil_div(p.n_pad, kWThreads);
+  p.n_bins = n_bins; p.n_groups = t.n_groups; p.bins_per_group = t.bins_per_group; p.bins_even = t.bins_even;
+  p.row_floats = t.row_floats;
+  int64_t blocks = g2g_ceil_div(p.n_pad, kWCells);
   p.counter = reinterpret_cast<unsigned int*>(workspace);
   p.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
   cudaStream_t st = (cudaStream_t)stream;
   G2G_CUDA_TRY(cudaMemsetAsync(p.counter, 0, 16, st));
-  weights_kernel<<<(unsigned)blocks, kWThreads, 0, st>>>(p);
+  const size_t smem = (size_t)n_bins * (kWCells + 1 + 4) * sizeof(double);
+  if (smem > 48 * 1024)
+    G2G_CUDA_TRY(cudaFuncSetAttribute(weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  weights_kernel<<<(unsigned)blocks, kWThreads, smem, st>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
 }

@@ -16,6 +16,9 @@ from ._lib import Side, c_f64
 N_SAMPLES = 50  # reference: generate_random_dataset(50, ...)  TimeSeriesPreprocessor.py:179
 
 
+_EPS_CACHE = {}
+
+
 def epsilon_table(n_bins, n_samples=N_SAMPLES, seed=1):
     """The fixed standard-normal table behind every interpolated bin of the reference.
 
@@ -25,15 +28,19 @@ def epsilon_table(n_bins, n_samples=N_SAMPLES, seed=1):
     shared by all genes.  A private generator seeded the same way gives the same mt19937 stream
     without touching the global RNG state.
     """
-    gen = torch.Generator(device="cpu")
-    gen.manual_seed(seed)
-    zero = torch.zeros((), dtype=torch.float64)
-    one = torch.ones((), dtype=torch.float64)
-    out = np.empty((n_bins, n_samples), dtype=np.float64)
-    for t in range(n_bins):
-        for n in range(n_samples):
-            out[t, n] = float(torch.normal(zero, one, generator=gen))
-    return out
+    key = (int(n_bins), int(n_samples), int(seed))
+    if key not in _EPS_CACHE:
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(seed)
+        zero = torch.zeros((), dtype=torch.float64)
+        one = torch.ones((), dtype=torch.float64)
+        out = np.empty((n_bins, n_samples), dtype=np.float64)
+        for t in range(n_bins):
+            for n in range(n_samples):
+                out[t, n] = float(torch.normal(zero, one, generator=gen))
+        out.setflags(write=False)
+        _EPS_CACHE[key] = out
+    return _EPS_CACHE[key]
 
 
 def transition_costs(free_params=(0.99, 0.1, 0.7), prohibit_case=False):
@@ -185,7 +192,13 @@ class AlignmentEngine:
         self.opt_cost = torch.empty(G, **f64)
         self.l_states = torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev)
         self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
+        self.fix_ws_bytes = self.lib.g2g_fixup_workspace_bytes(G, T)
+        self.fix_ws = torch.empty((self.fix_ws_bytes + 7) // 8, **f64)
         self.launches_per_run = 0
+        self._host_buf = None
+        self._side_stream = torch.cuda.Stream(device=dev)
+        self._ev_fork = torch.cuda.Event()
+        self._ev_join = torch.cuda.Event()
 
     def set_state_params(self, free_params):
         self.free_params = tuple(float(v) for v in free_params)
@@ -194,18 +207,24 @@ class AlignmentEngine:
     # -- stages -----------------------------------------------------------------------------
     def run_interpolation(self):
         lib, T, G = self.lib, self.n_bins, self.n_genes
-        st = _stream()
-        n = 0
-        for s in (self.ref, self.query):
+        cur = torch.cuda.current_stream()
+        # the two datasets' weight tables / pilot means are independent: fork the query side
+        self._ev_fork.record(cur)
+        self._side_stream.wait_event(self._ev_fork)
+        for s, stream in ((self.query, self._side_stream), (self.ref, cur)):
+            st = ctypes.c_void_p(stream.cuda_stream)
             _lib.check(lib.g2g_weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
                                        _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
             _lib.check(lib.g2g_pilot_mean(_ptr(s.X), s.n_cells, G, s.ld, _ptr(s.pilot), st), "g2g_pilot_mean")
-            n += 2
+        self._ev_join.record(self._side_stream)
+        cur.wait_event(self._ev_join)
+        st = _stream()
         _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
         _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
                                         _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
-                                        _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), st), "g2g_fixup_trends")
-        return n + 2
+                                        _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), _ptr(self.fix_ws),
+                                        self.fix_ws_bytes, st), "g2g_fixup_trends")
+        return 7  # 2 x (weights, pilot) + moments + partial reduce + fix-up
 
     def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None):
         """K4 on all genes (or ``gene_slice``).  ``dump=True`` also returns the dense matrices."""
@@ -252,14 +271,25 @@ class AlignmentEngine:
         self.launches_per_run = n + 1
         return self
 
+    RESULT_KEYS = ("opt_cost", "trends", "musigma", "align_len", "flags", "nnz", "align_str", "l_states")
+
     def results_to_host(self):
-        """One device->host transfer per result array (pinned staging, then a single sync)."""
-        keys = ("musigma", "trends", "nnz", "flags", "align_str", "align_len", "opt_cost", "l_states")
-        host = {}
-        for k in keys:
-            t = getattr(self, k)
-            h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
-            h.copy_(t, non_blocking=True)
-            host[k] = h
+        """All result arrays in ONE device->host copy: they are packed into a byte buffer on the
+        device (8-, 4-, then 1-byte element types so every view stays aligned) and land in a
+        pinned host buffer."""
+        parts = [getattr(self, k) for k in self.RESULT_KEYS]
+        packed = torch.cat([t.view(torch.uint8).reshape(-1) for t in parts])
+        if self._host_buf is None or self._host_buf.numel() != packed.numel():
+            self._host_buf = torch.empty(packed.numel(), dtype=torch.uint8, pin_memory=True)
+        self._host_buf.copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return {k: v.numpy() for k, v in host.items()}
+        raw = self._host_buf.numpy()
+        host, off = {}, 0
+        for k, t in zip(self.RESULT_KEYS, parts):
+            n = t.numel() * t.element_size()
+            host[k] = raw[off:off + n].view(_NP_DTYPES[t.dtype]).reshape(tuple(t.shape)).copy()
+            off += n
+        return host
+
+
+_NP_DTYPES = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}

@@ -103,7 +103,7 @@ int g2g_weights(const double* tau, int64_t n_cells, const double* points, const 
 /* ---------------------------------------------------------------------------------------------
  * K1a g2g_pilot_mean -- per-gene shift value a[g] (mean of a fixed strided sample of <= 64 rows).
  * Any value close to the gene's mean works: it only conditions the single-pass variance
- *   sum w (x - xbar)^2 = sum w (x-a)^2 - 2 (xbar-a) sum w (x-a) + (xbar-a)^2 sum w
+ *   sum w (x - xbar)^2 = sum w (x-a)^2 - 2 (xbar-a) (sum w x - a sum w) + (xbar-a)^2 sum w
  * which g2g_fixup_trends evaluates in f64 (the reference takes the variance around the
  * un-weighted whole-gene mean, TSP.py:171-172).
  */
@@ -118,8 +118,8 @@ int g2g_pilot_mean(const float* X, int64_t n_cells, int64_t n_genes, int64_t ldx
  *   X            f32 [n_cells][ldx] row major (cells x genes); ldx % 4 == 0 and X 16-byte aligned
  *                (the matrix is streamed with TMA)
  *   wtab, pilot  from g2g_weights / g2g_pilot_mean
- *   part_f64     f64 out [n_split][2*n_bins+1][g_stride]: per split, sum w(x-a) per bin,
- *                sum w(x-a)^2 per bin, sum (x-a)
+ *   part_f64     f64 out [n_split][2*n_bins+1][g_stride]: per split, sum w x per bin,
+ *                sum w (x-a)^2 per bin, sum (x-a)
  *   part_i32     i32 out [n_split][n_bins][g_stride]: nnz per window k (p_k <= tau < p_{k+1}) for
  *                k < n_bins-1, and at index n_bins-1 the nnz of cells outside every window
  *   g_stride     >= n_genes
@@ -151,11 +151,15 @@ int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64
  *   trends    f64 out [n_genes][4][n_bins]: mean_trend_S, std_trend_S, mean_trend_T, std_trend_T
  *   nnz       i32 out [n_genes][2]
  *   flags     i32 out [n_genes]  (G2G_FLAG_*)
+ *   workspace >= g2g_fixup_workspace_bytes() bytes, 8-byte aligned (the per-split partial sums of
+ *             K1 are first added up in split order into it)
  */
+size_t g2g_fixup_workspace_bytes(int64_t g_stride, int32_t n_bins);
 int g2g_fixup_trends(const g2g_side_t* sides, const double* sum_w_ref, const double* sum_w_query,
                      const double* points, const double* eps_mean, const double* eps_std,
                      int64_t n_genes, int64_t g_stride, int32_t n_bins, double* musigma,
-                     double* trends, int32_t* nnz, int32_t* flags, void* stream);
+                     double* trends, int32_t* nnz, int32_t* flags, void* workspace,
+                     size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K4  g2g_cost_dp -- MML match cost + five-state DP + traceback + landscape, one warp per gene.

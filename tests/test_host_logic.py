@@ -58,23 +58,61 @@ def test_matched_points_equal_dp_cells_on_random_legal_strings():
         assert list(zip(S.tolist(), T.tolist())) == want, s
 
 
+class _FakeAligner:
+    """Just enough of RefQueryAligner for AligmentObj views: host result arrays without a GPU."""
+
+    def __init__(self, ref, T):
+        G = len(ref["alignment_str"])
+        self.gene_list = ["g%d" % k for k in range(G)]
+        self.n_artificial_time_points = T
+        self._gene_index = {g: k for k, g in enumerate(self.gene_list)}
+        self._aligned_state_params = (0.99, 0.1, 0.7)
+        self.pairs = Main._LazyPairs(self)
+        strs = [str(s).encode() for s in ref["alignment_str"]]
+        buf = np.zeros((G, 2 * T), dtype=np.uint8)
+        for g, b in enumerate(strs):
+            buf[g, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+        self._host = {
+            "align_str": buf, "align_len": np.array([len(b) for b in strs], dtype=np.int32),
+            "opt_cost": ref["opt_cost"], "l_states": ref["L_states"].reshape(G, -1).astype(np.uint8),
+            "musigma": np.stack([ref["intpl_means_S"], ref["intpl_stds_S"], ref["intpl_means_T"],
+                                 ref["intpl_stds_T"]], axis=1),
+            "trends": np.stack([ref["mean_trend_S"], ref["std_trend_S"], ref["mean_trend_T"], ref["std_trend_T"]],
+                               axis=1)}
+
+        class _TI:
+            interpolation_points = np.linspace(0, 1, T)
+
+        class _Eng:
+            eps = engine.epsilon_table(T)
+
+        self.TrajInt_R = self.TrajInt_Q = _TI()
+        self._engine = _Eng()
+
+    _series_pair = Main.RefQueryAligner._series_pair
+
+
 def test_aligment_obj_fields_from_reference_strings(golden_dir):
     ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
-    eps = engine.epsilon_table(14)
-    pts = np.linspace(0, 1, 14)
+    al = _FakeAligner(ref, 14)
+    results = [Main.AligmentObj(al, g, al.gene_list[g]) for g in range(89)]
     for g in range(0, 89, 7):
-        S = SummaryTimeSeries("g", ref["intpl_means_S"][g], ref["intpl_stds_S"][g], ref["mean_trend_S"][g],
-                              ref["std_trend_S"][g], pts, eps)
-        T = SummaryTimeSeries("g", ref["intpl_means_T"][g], ref["intpl_stds_T"][g], ref["mean_trend_T"][g],
-                              ref["std_trend_T"][g], pts, eps)
-        dp = OrgAlign.DP5(None, g, S, T, str(ref["alignment_str"][g]), ref["opt_cost"][g], (0.99, 0.1, 0.7))
-        a = Main.AligmentObj(None, g, "g", S, T, dp, OrgAlign.AlignmentLandscape(dp, ref["L_states"][g], 14, 14))
+        a = results[g]
+        assert a.alignment_str == str(ref["alignment_str"][g])
         assert tuple(a.get_series_match_percentage()) == tuple(ref["match_percentage"][g])
+        assert [a.match_regions_S, a.match_regions_T, a.non_match_regions_S, a.non_match_regions_T] == \
+            json.loads(str(ref["regions"][g]))
         assert (np.asarray(a.landscape_obj.L_matrix_states) == ref["L_states"][g].astype("<U1")).all()
         assert a.fwd_DP.alignment_path == json.loads(str(ref["paths"][g]))
+        assert a.fwd_DP.opt_cost == ref["opt_cost"][g] == a.get_opt_alignment_cost()
+        assert a.bwd_DP is None and a.fwd_DP.S_len == 14 and a.fwd_DP.T_len == 14
+        a.cluster_id = 3                      # downstream code sets attributes on result objects
+        assert a.cluster_id == 3
+        with pytest.raises(AttributeError):
+            a.no_such_attribute
         if g < ref["data_bins_S"].shape[0]:
-            assert np.array_equal(np.asarray(S.data_bins), ref["data_bins_S"][g])
-            assert np.array_equal(S.Y, ref["data_bins_S"][g].flatten())
+            assert np.array_equal(np.asarray(a.S.data_bins), ref["data_bins_S"][g])
+            assert np.array_equal(a.S.Y, ref["data_bins_S"][g].flatten())
         # DE statistics table (scipy on the host) vs the reference's
         want = np.asarray(json.loads(str(ref["de_info"][g])))
         got = a.matched_region_DE_info.values.astype(float)
