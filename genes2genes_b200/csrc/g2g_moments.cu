@@ -16,6 +16,7 @@
 // f64 sums go to its own slot of `part_f64`.
 #include "g2g_common.cuh"
 #include <cuda.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -431,6 +432,10 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
     return G2G_ERR_UNSUPPORTED;
   }
   int grid = n_sm * occ;
+  if (const char* env = getenv("G2G_MOM_CTAS_PER_SM")) {  // tuning knob
+    int v = atoi(env);
+    if (v >= 1 && v <= occ) grid = n_sm * v;
+  }
   if (grid > items) grid = items;
   moments_kernel<TBE, GX><<<grid, kThreads, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());

@@ -2,6 +2,7 @@
 // K1a g2g_pilot_mean  per-gene shift value from a fixed strided row sample
 #include "g2g_common.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -95,11 +96,20 @@ __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams 
     s_last = (done == gridDim.x - 1);
   }
   __syncthreads();
-  if (s_last) {  // the last block to finish sums the per-block partials in block order
+  if (s_last) {  // the last block to finish sums the per-block partials: 16 interleaved chains per
+                 // bin (block b goes to chain b % 16, in block order), then the chains in order
     __threadfence();
+    for (int k = threadIdx.x; k < T * 16; k += kWThreads) {
+      const int t = k >> 4, q = k & 15;
+      double r = 0.0;
+      for (unsigned int b = q; b < gridDim.x; b += 16) r += p.partial[(size_t)b * T + t];
+      s_w[t][q] = r;
+    }
+    __syncthreads();
     for (int t = threadIdx.x; t < T; t += kWThreads) {
       double r = 0.0;
-      for (unsigned int b = 0; b < gridDim.x; ++b) r += p.partial[(size_t)b * T + t];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) r += s_w[t][q];
       p.sum_w[t] = r;
     }
   }
@@ -147,6 +157,10 @@ extern "C" int g2g_layout(int64_t n_cells, int32_t n_bins, g2g_layout_t* out) {
   int64_t min_item = g2g_round_up(6 * (5 * (int64_t)t.bins_per_group + 2), G2G_CELL_TILE);
   int64_t by_n = g2g_round_up(g2g_ceil_div(n_cells, 64), G2G_CELL_TILE);
   int64_t item = by_n > min_item ? by_n : min_item;
+  if (const char* env = getenv("G2G_ITEM_CELLS")) {  // tuning knob (must be the same for every call of a run)
+    int64_t v = atoll(env);
+    if (v >= G2G_CELL_TILE) item = g2g_round_up(v, G2G_CELL_TILE);
+  }
   if (item > out->n_pad) item = out->n_pad;
   out->cells_per_item = item;
   out->n_split = g2g_ceil_div(out->n_pad, item);
