@@ -53,28 +53,33 @@ __device__ __forceinline__ Five shfl_up5(const Five& a) {
   return r;
 }
 
-// first minimum of (src[k] + c) + tr[k], k = 0..4  (list.index(min(list)), OrgAlign.py:428-437)
+// first minimum of five candidates (list.index(min(list)), OrgAlign.py:428-437) as a tournament:
+// a later candidate wins only when strictly smaller, so ties keep the lowest index
+__device__ __forceinline__ void first_min5(double c0, double c1, double c2, double c3, double c4, double& best,
+                                           int& arg) {
+  const bool p01 = c1 < c0, p23 = c3 < c2;
+  const double m01 = p01 ? c1 : c0, m23 = p23 ? c3 : c2;
+  const int a01 = p01 ? 1 : 0, a23 = p23 ? 3 : 2;
+  const bool pq = m23 < m01;
+  const double m = pq ? m23 : m01;
+  const int a = pq ? a23 : a01;
+  const bool p4 = c4 < m;
+  best = p4 ? c4 : m;
+  arg = p4 ? 4 : a;
+}
+// candidates (src[k] + c) + tr[k], k = 0..4, in the reference's evaluation order (OrgAlign.py:352-374)
 __device__ __forceinline__ void best5(const Five& src, double c, const double* tr, double& best, int& arg) {
-  best = (src.v[0] + c) + tr[0];
-  arg = 0;
-#pragma unroll
-  for (int k = 1; k < 5; ++k) {
-    double cand = (src.v[k] + c) + tr[k];
-    if (cand < best) { best = cand; arg = k; }
-  }
+  first_min5((src.v[0] + c) + tr[0], (src.v[1] + c) + tr[1], (src.v[2] + c) + tr[2], (src.v[3] + c) + tr[3],
+             (src.v[4] + c) + tr[4], best, arg);
 }
 __device__ __forceinline__ void best5_gap(const Five& src, const double* tr, double& best, int& arg) {
   // gap cells cost 0.0 (OrgAlign.py:473-474, 499-500); (x + 0.0) + t == x + t bit for bit
-  best = src.v[0] + tr[0];
-  arg = 0;
-#pragma unroll
-  for (int k = 1; k < 5; ++k) {
-    double cand = src.v[k] + tr[k];
-    if (cand < best) { best = cand; arg = k; }
-  }
+  first_min5(src.v[0] + tr[0], src.v[1] + tr[1], src.v[2] + tr[2], src.v[3] + tr[3], src.v[4] + tr[4], best, arg);
 }
 
-template <int B>
+// FULL = false is the production path (cost from trends, compact outputs only); FULL = true also
+// honours cost_in and the dense dump pointers (verification, on-demand per-gene matrices).
+template <int B, bool FULL>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_constant__ DpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int T = p.n_bins;
@@ -95,12 +100,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
 
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
   const double* tr = p.trends + (size_t)g * 4 * T;
-  const bool have_cost = p.cost_in != nullptr;
+  const bool have_cost = FULL && p.cost_in != nullptr;
   const double* cin = have_cost ? p.cost_in + (size_t)g * T * T : nullptr;
-  double* cout = p.cost_out ? p.cost_out + (size_t)g * T * T : nullptr;
-  double* mout = p.mats_out ? p.mats_out + (size_t)g * 5 * nC * nC : nullptr;
-  int8_t* bout = p.bp_out ? p.bp_out + (size_t)g * 5 * nC * nC : nullptr;
-  double* lout = p.l_out ? p.l_out + (size_t)g * nC * nC : nullptr;
+  double* cout = (FULL && p.cost_out) ? p.cost_out + (size_t)g * T * T : nullptr;
+  double* mout = (FULL && p.mats_out) ? p.mats_out + (size_t)g * 5 * nC * nC : nullptr;
+  int8_t* bout = (FULL && p.bp_out) ? p.bp_out + (size_t)g * 5 * nC * nC : nullptr;
+  double* lout = (FULL && p.l_out) ? p.l_out + (size_t)g * nC * nC : nullptr;
 
   // ---- prologue: per-bin terms of the closed-form cost -----------------------------------
   for (int t = lane; t < T; t += 32) {
@@ -171,6 +176,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
 
   const int n_lanes = (nC + B - 1) / B;  // lanes that own at least one column
   const int n_steps = T + n_lanes - 1;
+  double fin_best = 0.0;  // min over the five matrices at (T, T) and its state, set by the owning lane
+  int fin_state = 0;
   for (int s = 0; s < n_steps; ++s) {
     Five nbr = shfl_up5(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
     const int i = s - lane + 1;
@@ -183,11 +190,13 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
         if (j > T) break;
         Five cur;
         int lstate;
+        double lbest;
         if (j == 0) {
           // column 0: only I is finite (OrgAlign.py:287-318)
           cur.v[0] = inf; cur.v[1] = inf; cur.v[2] = inf; cur.v[3] = inf;
           cur.v[4] = up[b].v[4] + (i == 1 ? p.start[0] : p.trans[4 * 5 + 4]);
           lstate = 4;
+          lbest = cur.v[4];
           if (bout) {
 #pragma unroll
             for (int k = 0; k < 5; ++k) bout[(size_t)k * nC * nC + (size_t)i * nC] = (k == 4) ? 4 : -1;
@@ -215,7 +224,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
           best5_gap(left, &p.trans[15], cur.v[3], ad);
           best5_gap(up[b], &p.trans[20], cur.v[4], ai);
           bp[(size_t)(i - 1) * T + (j - 1)] = (uint16_t)(am | (aw << 3) | (av << 6) | (ad << 9) | (ai << 12));
-          double lbest = cur.v[0];
+          lbest = cur.v[0];
           lstate = 0;
 #pragma unroll
           for (int k = 1; k < 5; ++k)
@@ -227,11 +236,12 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
           }
         }
         ls[(size_t)i * nC + j] = (uint8_t)lstate;
+        if (i == T && j == T) { fin_best = lbest; fin_state = lstate; }
         if (mout) {
 #pragma unroll
           for (int k = 0; k < 5; ++k) mout[(size_t)k * nC * nC + (size_t)i * nC + j] = cur.v[k];
         }
-        if (lout) lout[(size_t)i * nC + j] = cur.v[lstate];
+        if (lout) lout[(size_t)i * nC + j] = lbest;
         diag = up[b];   // (i-1, j) is the diagonal input of column j+1
         left = cur;     // (i, j) is its left input
         up[b] = cur;
@@ -243,18 +253,10 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
 
   // ---- traceback (OrgAlign.py:539-607) by the lane that owns column T ------------------------
   const int owner = T / B;
-  const int ob = T - owner * B;
   int len = 0;
   if (lane == owner) {
-    Five fin;
-#pragma unroll
-    for (int b = 0; b < B; ++b)
-      if (b == ob) fin = up[b];
-    double best = fin.v[0];
-    int state = 0;
-#pragma unroll
-    for (int k = 1; k < 5; ++k)
-      if (fin.v[k] < best) { best = fin.v[k]; state = k; }
+    const double best = fin_best;
+    int state = fin_state;
     p.opt_cost[g] = best;
     int i = T, j = T;
     const int cap = 2 * T;
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
       else prev = (bp[(size_t)(i - 1) * T + (j - 1)] >> (3 * state)) & 7;
       if (i == 0) state = 3;
       if (j == 0 && i > 0) state = 4;
-      sbuf[cap - 1 - len] = "MWVDI"[state];
+      sbuf[cap - 1 - len] = (uint8_t)((0x494456574dULL >> (8 * state)) & 0xff);  // "MWVDI"[state]
       ++len;
       if (state == 0) { --i; --j; }
       else if (state == 1 || state == 3) { --j; }
@@ -282,16 +284,22 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
   for (int k = lane; k < nC * nC; k += 32) lo[k] = ls[k];
 }
 
-template <int B>
-int launch_dp(const DpParams& p, cudaStream_t stream) {
+template <int B, bool FULL>
+int launch_dp_mode(const DpParams& p, cudaStream_t stream) {
   size_t smem = dp_smem_per_warp(p.n_bins) * kWarpsPerBlock;
   if (smem > 48 * 1024) {
-    G2G_CUDA_TRY(cudaFuncSetAttribute(dp_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    G2G_CUDA_TRY(cudaFuncSetAttribute(dp_kernel<B, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
   unsigned blocks = (unsigned)g2g_ceil_div(p.n_genes, kWarpsPerBlock);
-  dp_kernel<B><<<blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+  dp_kernel<B, FULL><<<blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
+}
+
+template <int B>
+int launch_dp(const DpParams& p, cudaStream_t stream) {
+  const bool full = p.cost_in || p.cost_out || p.mats_out || p.bp_out || p.l_out;
+  return full ? launch_dp_mode<B, true>(p, stream) : launch_dp_mode<B, false>(p, stream);
 }
 
 }  // namespace

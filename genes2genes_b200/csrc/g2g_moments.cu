@@ -79,7 +79,8 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                : "memory");
 }
 #ifndef G2G_MOM_MIN_BLOCKS
-#define G2G_MOM_MIN_BLOCKS 1   // CTAs per SM the register / shared-memory budget is sized for (tuning knob)
+#define G2G_MOM_MIN_BLOCKS 2   // CTAs per SM the register / shared-memory budget is sized for (tuning knob;
+                               // 2 measured faster than 1 on B200, profiles/r01_k1_item_size_sweep.txt)
 #endif
 
 template <int TBE, int GX>
@@ -92,7 +93,9 @@ struct Cfg {
   static constexpr int WBYTES = kCellTile * RF * 4;
   static constexpr int STAGE_BYTES = XBYTES + WBYTES;
   // the cross-warp reduction goes through a shared staging area, in kPasses slices of kRows rows
-  static constexpr int kStagingCap = (G2G_MOM_MIN_BLOCKS >= 2 ? 16 : 64) * 1024;
+  // two CTAs per SM while the register tile leaves room (<= 128 registers without spills)
+  static constexpr int kMinBlocks = (G2G_MOM_MIN_BLOCKS >= 2 && 2 * TBE * GX <= 64) ? 2 : 1;
+  static constexpr int kStagingCap = (kMinBlocks >= 2 ? 16 : 64) * 1024;
   static constexpr int kPasses = (kConsumerWarps * NQ * GT * 4 + kStagingCap - 1) / kStagingCap;
   static constexpr int kRows = (NQ + kPasses - 1) / kPasses;
   static constexpr int STAGING_BYTES = kConsumerWarps * kRows * GT * 4;
@@ -128,7 +131,7 @@ __device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_f
 __device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
 template <int TBE, int GX>
-__global__ void __launch_bounds__(kThreads, G2G_MOM_MIN_BLOCKS) moments_kernel(const __grid_constant__ MomParams p) {
+__global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_kernel(const __grid_constant__ MomParams p) {
   using C = Cfg<TBE, GX>;
   constexpr int NP = C::NP;
   constexpr int kCellUnroll = (2 * TBE * GX <= 64) ? 2 : 1;
@@ -420,7 +423,7 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
                        8 * 8 + (8 + 2) * 4 + 128;
   // as many stages (<= 8, >= 2) as fit the shared memory of G2G_MOM_MIN_BLOCKS CTAs per SM
   int stages = 8;
-  const size_t budget = (size_t)(G2G_MOM_MIN_BLOCKS >= 2 ? 110 : 200) * 1024;
+  const size_t budget = (size_t)(C::kMinBlocks >= 2 ? 110 : 200) * 1024;
   while (stages > 2 && fixed + (size_t)stages * C::STAGE_BYTES > budget) --stages;
   p.n_stages = stages;
   const size_t smem = fixed + (size_t)stages * C::STAGE_BYTES;

@@ -153,8 +153,9 @@ extern "C" int g2g_layout(int64_t n_cells, int32_t n_bins, g2g_layout_t* out) {
   out->n_pad = g2g_round_up(n_cells, G2G_CELL_TILE);
   // one work item = cells_per_item rows x one gene tile.  Smaller items balance better over the
   // persistent CTAs but write more partial sums ((5T+2)/cells_per_item of the X bytes streamed);
-  // the floor keeps that near 16%, and large inputs are cut into ~64 ranges.
-  int64_t min_item = g2g_round_up(6 * (5 * (int64_t)t.bins_per_group + 2), G2G_CELL_TILE);
+  // the floor keeps that near 8%, and large inputs are cut into ~64 ranges
+  // (measured on C2: profiles/r01_k1_item_size_sweep.txt).
+  int64_t min_item = g2g_round_up(12 * (5 * (int64_t)t.bins_per_group + 2), G2G_CELL_TILE);
   int64_t by_n = g2g_round_up(g2g_ceil_div(n_cells, 64), G2G_CELL_TILE);
   int64_t item = by_n > min_item ? by_n : min_item;
   if (const char* env = getenv("G2G_ITEM_CELLS")) {  // tuning knob (must be the same for every call of a run)

@@ -280,7 +280,7 @@ class AlignmentEngine:
         parts = [getattr(self, k) for k in self.RESULT_KEYS]
         packed = torch.cat([t.view(torch.uint8).reshape(-1) for t in parts])
         if self._host_buf is None or self._host_buf.numel() != packed.numel():
-            self._host_buf = torch.empty(packed.numel(), dtype=torch.uint8, pin_memory=True)
+            self._host_buf = _pinned_buffer(packed.numel())
         self._host_buf.copy_(packed, non_blocking=True)
         torch.cuda.current_stream().synchronize()
         raw = self._host_buf.numpy()
@@ -290,6 +290,20 @@ class AlignmentEngine:
             host[k] = raw[off:off + n].view(_NP_DTYPES[t.dtype]).reshape(tuple(t.shape)).copy()
             off += n
         return host
+
+
+_PINNED = {}
+
+
+def _pinned_buffer(n_bytes):
+    """Pinned staging buffers are expensive to create (cudaHostAlloc); keep one per size."""
+    buf = _PINNED.get(n_bytes)
+    if buf is None:
+        if len(_PINNED) > 8:
+            _PINNED.clear()
+        buf = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
+        _PINNED[n_bytes] = buf
+    return buf
 
 
 _NP_DTYPES = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}
