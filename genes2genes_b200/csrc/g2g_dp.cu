@@ -206,10 +206,15 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
           if (have_cost) {
             c = cin[(size_t)(i - 1) * T + (j - 1)];
           } else {
-            double d = t_mu - s_mu[b];
-            double d2 = d * d;
-            double a = (t_var + d2) * s_ivar[b] + (s_var[b] + d2) * t_ivar - 2.0;
-            c = (p.half_n * a - p.two_c + s_ln[b] + t_ln) * p.inv_4n;
+            // explicit roundings: both kernel instantiations (and every compiler version) evaluate
+            // the closed form with the same operations, so dumped costs are the costs the DP used
+            const double d = __dsub_rn(t_mu, s_mu[b]);
+            const double d2 = __dmul_rn(d, d);
+            const double a = __fma_rn(__dadd_rn(t_var, d2), s_ivar[b],
+                                      __fma_rn(__dadd_rn(s_var[b], d2), t_ivar, -2.0));
+            double u = __fma_rn(p.half_n, a, -p.two_c);
+            u = __dadd_rn(__dadd_rn(u, s_ln[b]), t_ln);
+            c = __dmul_rn(u, p.inv_4n);
           }
           if (cout) cout[(size_t)(i - 1) * T + (j - 1)] = c;
           int am, aw, av, ad, ai;
