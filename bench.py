@@ -258,12 +258,12 @@ def run_b200(args):
         flush_buf.fill_(1)
         graph.replay() if graph is not None else step()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(0.3)
+    if world > 1:
+        dist.barrier()   # after rank 0 started its clock sampler, so all ranks enter the timed loop together
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     torch.cuda.synchronize()

@@ -344,8 +344,18 @@ class RefQueryAligner:
     ``.obs['time']`` in [0, 1], ``.var_names`` and ``.obs_names``.
     """
 
-    def __init__(self, *args, device=None, verbose=True):
+    def __init__(self, *args, device=None, verbose=True, distributed=False):
+        """``distributed=True`` (inside an initialised ``torch.distributed`` job, one process per GPU):
+        this rank aligns its contiguous block of ``gene_list`` and ``align_all_pairs`` gathers every
+        rank's result records to rank 0, whose ``results`` then cover the whole gene list; the other
+        ranks keep the results of their own block."""
         self._verbose = verbose
+        self._dist = None
+        if distributed:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                self._dist = (dist.get_rank(), dist.get_world_size())
+                self._verbose = verbose and self._dist[0] == 0
         self._say("===============================================================================================================")
         self._say("Genes2Genes (" + __version__ + ")")
         self._say("Dynamic programming alignment of gene pseudotime trajectories using a bayesian information-theoretic framework")
@@ -365,6 +375,13 @@ class RefQueryAligner:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
         adata_ref, adata_query, gene_list, n_bins = args[0], args[1], args[2], args[3]
         self.adata_ref_full, self.adata_query_full = adata_ref, adata_query
+        self._all_genes = list(gene_list)
+        self._shard = (0, len(gene_list))
+        if self._dist is not None:
+            from . import distributed as _distributed
+            self._shard = _distributed.shard_range(len(gene_list), *self._dist)
+            gene_list = self._all_genes[self._shard[0]:self._shard[1]]
+        self._local_genes = list(gene_list)
         self.gene_list = gene_list
         self.n_artificial_time_points = int(n_bins)
         self.ref_time = np.asarray(adata_ref.obs["time"], dtype=np.float64)
@@ -385,7 +402,7 @@ class RefQueryAligner:
             Xr = self._pack(adata_ref, self.TrajInt_R.order)
             Xq = self._pack(adata_query, self.TrajInt_Q.order)
             self._engine = _engine.AlignmentEngine(
-                Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(gene_list),
+                Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(self._local_genes),
                 self.n_artificial_time_points, self.TrajInt_R.kernel_denominators(),
                 self.TrajInt_Q.kernel_denominators(), self.state_params, self.device)
         self._say("Interpolator initialization completed")
@@ -402,11 +419,11 @@ class RefQueryAligner:
     def _pack(self, adata, order):
         """``adata[order][:, gene_list].X`` as a packed f32 device matrix."""
         var_names = [str(v) for v in adata.var_names]
-        if list(self.gene_list) == var_names:
+        if list(self._local_genes) == var_names:
             gene_idx = None
         else:
             pos = {g: k for k, g in enumerate(var_names)}
-            gene_idx = np.asarray([pos[g] for g in self.gene_list], dtype=np.int32)
+            gene_idx = np.asarray([pos[g] for g in self._local_genes], dtype=np.int32)
         X = adata.X
         identity = bool(np.all(order[1:] > order[:-1])) if len(order) > 1 else True
         row_order = None if identity else order
@@ -451,7 +468,10 @@ class RefQueryAligner:
                 eng.run_interpolation()
                 self._interp = True
             eng.run_dp()
-            self._host = eng.results_to_host()
+            if self._dist is None:
+                self._host = eng.results_to_host()
+            else:
+                self._host = self._gather_results()
         self._aligned_state_params = tuple(self.state_params)
         bad = np.nonzero(self._host["flags"] & _FLAG_BAD_SIGMA)[0]
         if len(bad):
@@ -460,6 +480,44 @@ class RefQueryAligner:
                              "(GreaterThan(lower_bound=0.0)); gene %r has a zero or invalid interpolated "
                              "standard deviation (%d gene(s) affected)" % (g, len(bad)))
         return self._host
+
+    def _gather_results(self):
+        """The one collective of the path: every rank's per-gene records go to rank 0 (NCCL gather)."""
+        import torch
+        import torch.distributed as dist
+        from . import distributed as D
+        rank, world = self._dist
+        eng, T = self._engine, self.n_artificial_time_points
+        n_all = len(self._all_genes)
+        per = -(-n_all // world)
+        padded = {}
+        for k in D.RECORD_KEYS:
+            t = getattr(eng, k)
+            buf = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+            buf[:t.shape[0]] = t
+            padded[k] = buf
+        send = D.pack_records(padded)
+        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
+        dist.gather(send, recv, dst=0)
+        if rank != 0:
+            return eng.results_to_host()
+        tmpl = D.record_templates(per, T)
+        parts = []
+        for r, b in enumerate(recv):
+            lo, hi = D.shard_range(n_all, r, world)
+            rec = D.unpack_records(b, tmpl)
+            parts.append({k: v[:hi - lo].cpu().numpy() for k, v in rec.items()})
+        self.gene_list = self._all_genes                    # rank 0 now holds every gene's result
+        self._gene_index = {g: k for k, g in enumerate(self.gene_list)}
+        self._shard = (0, n_all)
+        self._gathered = True
+        return {k: np.concatenate([p[k] for p in parts]) for k in D.RECORD_KEYS}
+
+    def _device_trends(self, idx):
+        """Trend vectors of one gene as a [1, 4, T] device tensor (from the gathered host copy when
+        the gene belongs to another rank's block)."""
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(self._host["trends"][idx:idx + 1])).to(self.device)
 
     def _series_pair(self, idx):
         if self._host is None:
@@ -484,7 +542,7 @@ class RefQueryAligner:
             self._run_batch()
         with torch.cuda.device(self.device):
             eng.set_state_params(self.state_params)
-            out = eng.run_dp(dump=True, gene_slice=slice(idx, idx + 1))
+            out = eng.run_dp(trends=self._device_trends(idx), dump=True)
             torch.cuda.current_stream().synchronize()
         d = {k: out[k][0].cpu().numpy() for k in ("cost", "mats", "bp", "L")}
         # null / match_len terms of OrgAlign.py:486-494 in closed form
@@ -516,7 +574,7 @@ class RefQueryAligner:
         eng = self._engine
         with torch.cuda.device(self.device):
             eng.set_state_params(self.state_params)
-            out = eng.run_dp(gene_slice=slice(gene_idx, gene_idx + 1))
+            out = eng.run_dp(trends=self._device_trends(gene_idx), dump=False, force_new=True)
             torch.cuda.current_stream().synchronize()
         one = {k: out[k].cpu().numpy() for k in ("align_str", "align_len", "opt_cost", "l_states")}
         view = {k: _Shift(one[k], gene_idx) for k in one}

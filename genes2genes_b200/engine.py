@@ -226,15 +226,16 @@ class AlignmentEngine:
                                         self.fix_ws_bytes, st), "g2g_fixup_trends")
         return 7  # 2 x (weights, pilot) + moments + partial reduce + fix-up
 
-    def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None):
-        """K4 on all genes (or ``gene_slice``).  ``dump=True`` also returns the dense matrices."""
+    def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None, force_new=False):
+        """K4 on all genes (or ``gene_slice`` / the given ``trends``).  ``dump=True`` also returns the
+        dense matrices; results go to fresh tensors unless this is the plain whole-batch run."""
         lib, T = self.lib, self.n_bins
         trends = self.trends if trends is None else trends
         if gene_slice is not None:
             trends = trends[gene_slice].contiguous()
         G = int(trends.shape[0])
         dev = self.device
-        if gene_slice is None and not dump and cost_in is None:
+        if gene_slice is None and not dump and cost_in is None and not force_new and trends is self.trends:
             out = dict(align_str=self.align_str, align_len=self.align_len, opt_cost=self.opt_cost,
                        l_states=self.l_states)
         else:

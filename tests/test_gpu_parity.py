@@ -309,3 +309,51 @@ def test_public_api_matches_reference_golden(golden_dir):
     aligner.state_params = [0.95, 0.2, 0.6]
     one = aligner.align_single_pair(5)
     assert one.gene == sub[5] and len(one.alignment_str) >= 14
+
+
+_DIST_WORKER = r"""
+import os, sys
+sys.path.insert(0, %r)
+import numpy as np, torch, torch.distributed as dist
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=torch.device("cuda", int(os.environ["LOCAL_RANK"])))
+from genes2genes_b200 import Main, synthetic
+from genes2genes_b200.anndata_lite import AnnDataLite
+G, nr, nq, T = 203, 1500, 1300, 14
+Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=0.85, seed=21)
+al = Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), AnnDataLite(Xq, tq, genes), genes, T, verbose=False, distributed=True)
+al.align_all_pairs()
+if rank == 0:
+    single = Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), AnnDataLite(Xq, tq, genes), genes, T, verbose=False)
+    single.align_all_pairs()
+    assert [a.gene for a in al.results] == genes
+    for k in single._host:   # sharded results byte-identical to the single-GPU run (SURVEY.md 8(e))
+        assert np.array_equal(single._host[k], al._host[k]), k
+    a = al.results_map[genes[-1]]          # a gene aligned by the last rank, served on rank 0
+    assert a.alignment_str == single.results_map[genes[-1]].alignment_str
+    assert np.array_equal(np.asarray(a.fwd_DP.DP_M_matrix), np.asarray(single.results[-1].fwd_DP.DP_M_matrix))
+    print("DIST_OK", world, len(al.results))
+else:
+    assert len(al.results) == len(al.gene_list) < G
+dist.barrier()
+dist.destroy_process_group()
+"""
+
+
+def test_distributed_api_matches_single_gpu(tmp_path):
+    """Gene-sharded run over all visible GPUs (>= 2) equals the single-GPU run bytewise."""
+    import subprocess
+    import sys
+    torch = _torch()
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs at least 2 GPUs")
+    n = 2 if n < 4 else (4 if n < 8 else 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "w.py"
+    script.write_text(_DIST_WORKER % root)
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=%d" % n,
+                          "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
+                         capture_output=True, text=True, timeout=600)
+    assert "DIST_OK %d 203" % n in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
