@@ -341,6 +341,7 @@ def run_b200(args):
                                   {"cuda_graph": graph is not None, "wall_s_timed_region": wall}),
             "e2e": {"value": world * G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t * 1e3, "steps": len(e2e_ms),
+                    "ms_each": [round(v, 3) for v in e2e_ms],
                     "what": "Main.RefQueryAligner(...) + align_all_pairs() from pinned host arrays to host result objects"},
             "gpu_launches": eng.launches_per_run * args.steps,
             "roofline": {"kernel": "moments_kernel (K1 g2g_moments)", "bound": "hbm", "achieved": achieved,

@@ -165,8 +165,8 @@ class AligmentObj:
         "match_percentage_T": "compute_series_match_percentage",
     }
 
-    def __init__(self, aligner, gene_idx, gene, host=None):
-        self._aligner = aligner
+    def __init__(self, store, gene_idx, gene, host=None):
+        self._store = store
         self._gene_idx = gene_idx
         self._host = host
         self.gene = gene
@@ -183,20 +183,20 @@ class AligmentObj:
         return self.__dict__[name]
 
     def _results(self):
-        return self._aligner._host if self._host is None else self._host
+        return self._store.host if self._host is None else self._host
 
     def _load_str(self):
         h, idx = self._results(), self._gene_idx
         self.alignment_str = h["align_str"][idx, :int(h["align_len"][idx])].tobytes().decode("ascii")
 
     def _load_series(self):
-        self.S, self.T = self._aligner.pairs[self.gene]
+        self.S, self.T = self._store.pairs[self.gene]
 
     def _load_core(self):
-        al, idx, h = self._aligner, self._gene_idx, self._results()
-        nT = al.n_artificial_time_points
-        dp = orgalign.DP5(al, idx, self.S, self.T, self.alignment_str, np.float64(h["opt_cost"][idx]),
-                          al._aligned_state_params)
+        st, idx, h = self._store, self._gene_idx, self._results()
+        nT = st.n_bins
+        dp = orgalign.DP5(st, idx, self.S, self.T, self.alignment_str, np.float64(h["opt_cost"][idx]),
+                          st.state_params if self._host is None else self._host["state_params"])
         self.fwd_DP = dp
         self.landscape_obj = orgalign.AlignmentLandscape(dp, h["l_states"][idx].reshape(nT + 1, nT + 1), nT, nT)
 
@@ -209,7 +209,7 @@ class AligmentObj:
         s = self.alignment_str
         n_m, n_v, n_w = s.count("M"), s.count("V"), s.count("W")
         self.match_percentage = round(((n_m + n_v + n_w) / len(s)) * 100, 2)
-        n_bins = self._aligner.n_artificial_time_points  # len(T.data_bins) == len(S.data_bins)
+        n_bins = self._store.n_bins  # len(T.data_bins) == len(S.data_bins)
         self.match_percentage_T = round(((n_m + n_v) / n_bins) * 100, 2)
         self.match_percentage_S = round(((n_m + n_w) / n_bins) * 100, 2)
 
@@ -325,15 +325,72 @@ class _LazyPairs(dict):
     """``aligner.pairs``: gene -> [S, T] interpolated series, filled on demand from the batch
     (the reference memoises ``run_interpolation`` per gene here, Main.py:417-418)."""
 
-    def __init__(self, aligner):
+    def __init__(self, store):
         super().__init__()
-        self._aligner = aligner
+        self._store = store
 
     def __missing__(self, gene):
-        idx = self._aligner._gene_index[gene]
-        st = self._aligner._series_pair(idx)
+        st = self._store.series_pair(self._store.gene_index[gene])
         self[gene] = st
         return st
+
+
+class _ResultStore:
+    """Host copy of one batch's compact results plus the little state needed to serve every
+    ``AligmentObj`` attribute.  It owns no batch device buffers and does not reference the aligner, so
+    dropping the aligner frees its GPU memory at once while result objects stay usable."""
+
+    def __init__(self, host, gene_list, n_bins, eps, points_ref, points_query, state_params, device):
+        self.host = host
+        self.gene_list = gene_list
+        self.gene_index = {g: k for k, g in enumerate(gene_list)}
+        self.n_bins = int(n_bins)
+        self.eps = eps
+        self.points_ref, self.points_query = points_ref, points_query
+        self.state_params = tuple(state_params)
+        self.device = device
+        self.pairs = _LazyPairs(self)
+
+    def series_pair(self, idx):
+        h = self.host
+        ms, tr = h["musigma"][idx], h["trends"][idx]
+        gene = self.gene_list[idx]
+        S = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[0], ms[1], tr[0], tr[1], self.points_ref, self.eps)
+        T = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[2], ms[3], tr[2], tr[3], self.points_query, self.eps)
+        return [S, T]
+
+    def device_trends(self, idx):
+        import torch
+        return torch.as_tensor(np.ascontiguousarray(self.host["trends"][idx:idx + 1])).to(self.device)
+
+    def run_dp(self, idx, state_params, dump):
+        import torch
+        with torch.cuda.device(self.device):
+            out = _engine.run_cost_dp(self.device_trends(idx), self.n_bins, _engine.transition_costs(state_params),
+                                      _engine.start_costs(), _engine.model_constant(), dump=dump)
+            torch.cuda.current_stream().synchronize()
+        return out
+
+    def dense_dump(self, idx, state_params):
+        """Dense DP matrices / back-pointers / cost terms of one gene (K4 in dump mode)."""
+        out = self.run_dp(idx, state_params, dump=True)
+        d = {k: out[k][0].cpu().numpy() for k in ("cost", "mats", "bp", "L")}
+        # null / match_len terms of OrgAlign.py:486-494 in closed form (SURVEY.md 8(a) row 7)
+        tr = self.host["trends"][idx]
+        n = _engine.N_SAMPLES
+        K = n / 2.0 * np.log(2 * np.pi) + 1.0 - n * np.log(0.001)
+        C = _engine.model_constant(n)
+        mS, sS, mT, sT = tr[0][None, :], tr[1][None, :], tr[2][:, None], tr[3][:, None]
+        d2 = (mT - mS) ** 2
+        I_RS = K + n * np.log(sS) + n / 2.0
+        I_QT = K + n * np.log(sT) + n / 2.0
+        I_QS = K + n * np.log(sS) + n * (sT ** 2 + d2) / (2 * sS ** 2)
+        I_RT = K + n * np.log(sT) + n * (sS ** 2 + d2) / (2 * sT ** 2)
+        mod_S, mod_T = C - np.log(sS), C - np.log(sT)
+        null = (mod_S + I_RS + mod_T + I_QT) / (2 * n) + 0 * d2
+        match = 0.5 * ((mod_S + I_QS + I_RS) + (mod_T + I_RT + I_QT)) / (2 * n)
+        d["util"] = np.stack([null, match, d["cost"]])
+        return d
 
 
 class RefQueryAligner:
@@ -386,8 +443,7 @@ class RefQueryAligner:
         self.n_artificial_time_points = int(n_bins)
         self.ref_time = np.asarray(adata_ref.obs["time"], dtype=np.float64)
         self.query_time = np.asarray(adata_query.obs["time"], dtype=np.float64)
-        self._gene_index = {g: k for k, g in enumerate(gene_list)}
-        self.pairs = _LazyPairs(self)
+        self._store = None
         self.state_params = [0.99, 0.1, 0.7]  # same defaults as the reference (Main.py:218)
         self.no_extreme_cases = False
 
@@ -407,7 +463,6 @@ class RefQueryAligner:
                 self.TrajInt_Q.kernel_denominators(), self.state_params, self.device)
         self._say("Interpolator initialization completed")
         self._interp = None
-        self._host = None
         self._say("Aligner initialised to align trajectories of", adata_ref.shape[0], "reference cells &",
                   adata_query.shape[0], "query cells in terms of", len(self.gene_list), "genes")
 
@@ -459,6 +514,17 @@ class RefQueryAligner:
         return pd.DataFrame(np.asarray(X), columns=adata.var_names, index=adata.obs_names)
 
     # -- stages ---------------------------------------------------------------------------------------
+    @property
+    def _host(self):
+        return None if self._store is None else self._store.host
+
+    @property
+    def pairs(self):
+        """gene -> [S, T] interpolated series (reference: ``self.pairs``, Main.py:257, 417-418)."""
+        if self._store is None:
+            self._run_batch()
+        return self._store.pairs
+
     def _run_batch(self):
         import torch
         eng = self._engine
@@ -468,18 +534,17 @@ class RefQueryAligner:
                 eng.run_interpolation()
                 self._interp = True
             eng.run_dp()
-            if self._dist is None:
-                self._host = eng.results_to_host()
-            else:
-                self._host = self._gather_results()
-        self._aligned_state_params = tuple(self.state_params)
-        bad = np.nonzero(self._host["flags"] & _FLAG_BAD_SIGMA)[0]
+            host = eng.results_to_host() if self._dist is None else self._gather_results()
+        self._store = _ResultStore(host, self.gene_list, self.n_artificial_time_points, eng.eps,
+                                   self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
+                                   self.state_params, self.device)
+        bad = np.nonzero(host["flags"] & _FLAG_BAD_SIGMA)[0]
         if len(bad):
             g = self.gene_list[int(bad[0])]
             raise ValueError("Expected parameter scale of the interpolated distribution to be positive "
                              "(GreaterThan(lower_bound=0.0)); gene %r has a zero or invalid interpolated "
                              "standard deviation (%d gene(s) affected)" % (g, len(bad)))
-        return self._host
+        return host
 
     def _gather_results(self):
         """The one collective of the path: every rank's per-gene records go to rank 0 (NCCL gather)."""
@@ -508,77 +573,25 @@ class RefQueryAligner:
             rec = D.unpack_records(b, tmpl)
             parts.append({k: v[:hi - lo].cpu().numpy() for k, v in rec.items()})
         self.gene_list = self._all_genes                    # rank 0 now holds every gene's result
-        self._gene_index = {g: k for k, g in enumerate(self.gene_list)}
         self._shard = (0, n_all)
-        self._gathered = True
         return {k: np.concatenate([p[k] for p in parts]) for k in D.RECORD_KEYS}
 
-    def _device_trends(self, idx):
-        """Trend vectors of one gene as a [1, 4, T] device tensor (from the gathered host copy when
-        the gene belongs to another rank's block)."""
-        import torch
-        return torch.as_tensor(np.ascontiguousarray(self._host["trends"][idx:idx + 1])).to(self.device)
-
-    def _series_pair(self, idx):
-        if self._host is None:
-            self._run_batch()
-        h, eng = self._host, self._engine
-        ms, tr = h["musigma"][idx], h["trends"][idx]
-        gene = self.gene_list[idx]
-        S = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[0], ms[1], tr[0], tr[1],
-                                                     self.TrajInt_R.interpolation_points, eng.eps)
-        T = TimeSeriesPreprocessor.SummaryTimeSeries(gene, ms[2], ms[3], tr[2], tr[3],
-                                                     self.TrajInt_Q.interpolation_points, eng.eps)
-        return [S, T]
-
     def _make_result(self, idx, host=None):
-        return AligmentObj(self, idx, self.gene_list[idx], host)
-
-    def _dense_dump(self, idx):
-        """Dense DP matrices / back-pointers / cost terms of one gene (K4 in dump mode)."""
-        import torch
-        eng = self._engine
-        if self._host is None:
-            self._run_batch()
-        with torch.cuda.device(self.device):
-            eng.set_state_params(self.state_params)
-            out = eng.run_dp(trends=self._device_trends(idx), dump=True)
-            torch.cuda.current_stream().synchronize()
-        d = {k: out[k][0].cpu().numpy() for k in ("cost", "mats", "bp", "L")}
-        # null / match_len terms of OrgAlign.py:486-494 in closed form (SURVEY.md 8(a) row 7)
-        tr = self._host["trends"][idx]
-        n = _engine.N_SAMPLES
-        K = n / 2.0 * np.log(2 * np.pi) + 1.0 - n * np.log(0.001)
-        C = _engine.model_constant(n)
-        mS, sS, mT, sT = tr[0][None, :], tr[1][None, :], tr[2][:, None], tr[3][:, None]
-        d2 = (mT - mS) ** 2
-        I_RS = K + n * np.log(sS) + n / 2.0
-        I_QT = K + n * np.log(sT) + n / 2.0
-        I_QS = K + n * np.log(sS) + n * (sT ** 2 + d2) / (2 * sS ** 2)
-        I_RT = K + n * np.log(sT) + n * (sS ** 2 + d2) / (2 * sT ** 2)
-        mod_S, mod_T = C - np.log(sS), C - np.log(sT)
-        null = (mod_S + I_RS + mod_T + I_QT) / (2 * n) + 0 * d2
-        match = 0.5 * ((mod_S + I_QS + I_RS) + (mod_T + I_RT + I_QT)) / (2 * n)
-        d["util"] = np.stack([null, match, d["cost"]])
-        return d
+        return AligmentObj(self._store, idx, self.gene_list[idx], host)
 
     def run_interpolation(self, gene_idx):
         """[S, T] interpolated series of one gene (reference: Main.py:307-410)."""
         return self.pairs[self.gene_list[gene_idx]]
 
     def align_single_pair(self, gene_idx):
-        """Align one gene with the current ``state_params`` (reference: Main.py:413-432)."""
-        import torch
-        if self._host is None:
+        """Align one gene with the current ``state_params`` (reference: Main.py:413-432); the
+        interpolation of the batch is reused (the reference memoises it in ``pairs``)."""
+        if self._store is None:
             self._run_batch()
-        eng = self._engine
-        with torch.cuda.device(self.device):
-            eng.set_state_params(self.state_params)
-            out = eng.run_dp(trends=self._device_trends(gene_idx), dump=False, force_new=True)
-            torch.cuda.current_stream().synchronize()
-        one = {k: out[k].cpu().numpy() for k in ("align_str", "align_len", "opt_cost", "l_states")}
-        view = {k: _Shift(one[k], gene_idx) for k in one}
-        self._aligned_state_params = tuple(self.state_params)
+        params = tuple(self.state_params)
+        out = self._store.run_dp(gene_idx, params, dump=False)
+        view = {k: _Shift(out[k].cpu().numpy(), gene_idx) for k in ("align_str", "align_len", "opt_cost", "l_states")}
+        view["state_params"] = params
         return self._make_result(gene_idx, view)
 
     def align_all_pairs(self, concurrent=False, n_processes=None):

@@ -37,8 +37,8 @@ class FiveStateMachine:
 class DP5:
     """Per-gene DP result view (reference: OrgAlign.py:206-646)."""
 
-    def __init__(self, aligner, gene_idx, S, T, alignment_str, opt_cost, free_params):
-        self._aligner = aligner
+    def __init__(self, store, gene_idx, S, T, alignment_str, opt_cost, free_params):
+        self._store = store
         self._gene_idx = gene_idx
         self.S = S
         self.T = T
@@ -72,7 +72,7 @@ class DP5:
 
     def _dump(self):
         if self._dense is None:
-            self._dense = self._aligner._dense_dump(self._gene_idx)
+            self._dense = self._store.dense_dump(self._gene_idx, self._free_params)
         return self._dense
 
     def _mat(self, k):

@@ -158,6 +158,35 @@ def pack_csr(csr, row_order, gene_idx, n_all_genes, device):
     return out
 
 
+def run_cost_dp(trends, n_bins, trans, start, c_model, cost_in=None, dump=False, out=None):
+    """Enqueue K4 (``g2g_cost_dp``) for the genes of ``trends`` ([G, 4, T] f64 on the device) on the
+    current stream.  Needs no other device state, so per-gene dense dumps can be produced long after
+    the batch buffers are gone."""
+    lib = _lib.load()
+    T = int(n_bins)
+    G = int(trends.shape[0])
+    dev = trends.device
+    if out is None:
+        out = dict(align_str=torch.empty((G, 2 * T), dtype=torch.uint8, device=dev),
+                   align_len=torch.empty(G, dtype=torch.int32, device=dev),
+                   opt_cost=torch.empty(G, dtype=torch.float64, device=dev),
+                   l_states=torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev))
+    cost_out = mats = bp = l_out = None
+    if dump:
+        cost_out = torch.empty((G, T, T), dtype=torch.float64, device=dev)
+        mats = torch.empty((G, 5, T + 1, T + 1), dtype=torch.float64, device=dev)
+        bp = torch.empty((G, 5, T + 1, T + 1), dtype=torch.int8, device=dev)
+        l_out = torch.empty((G, T + 1, T + 1), dtype=torch.float64, device=dev)
+        out.update(cost=cost_out, mats=mats, bp=bp, L=l_out)
+    trans_c = (c_f64 * 25)(*np.asarray(trans, dtype=np.float64).reshape(-1).tolist())
+    start_c = (c_f64 * 3)(*np.asarray(start, dtype=np.float64).tolist())
+    _lib.check(lib.g2g_cost_dp(_ptr(trends), G, T, trans_c, start_c, float(c_model), N_SAMPLES, _ptr(cost_in),
+                               _ptr(out["align_str"]), _ptr(out["align_len"]), _ptr(out["opt_cost"]),
+                               _ptr(out["l_states"]), _ptr(cost_out), _ptr(mats), _ptr(bp), _ptr(l_out),
+                               _stream()), "g2g_cost_dp")
+    return out
+
+
 class AlignmentEngine:
     """Runs the whole hot path for one (reference, query) pair of packed device matrices.
 
@@ -229,34 +258,15 @@ class AlignmentEngine:
     def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None, force_new=False):
         """K4 on all genes (or ``gene_slice`` / the given ``trends``).  ``dump=True`` also returns the
         dense matrices; results go to fresh tensors unless this is the plain whole-batch run."""
-        lib, T = self.lib, self.n_bins
         trends = self.trends if trends is None else trends
         if gene_slice is not None:
             trends = trends[gene_slice].contiguous()
-        G = int(trends.shape[0])
-        dev = self.device
+        out = None
         if gene_slice is None and not dump and cost_in is None and not force_new and trends is self.trends:
             out = dict(align_str=self.align_str, align_len=self.align_len, opt_cost=self.opt_cost,
                        l_states=self.l_states)
-        else:
-            out = dict(align_str=torch.empty((G, 2 * T), dtype=torch.uint8, device=dev),
-                       align_len=torch.empty(G, dtype=torch.int32, device=dev),
-                       opt_cost=torch.empty(G, dtype=torch.float64, device=dev),
-                       l_states=torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev))
-        cost_out = mats = bp = l_out = None
-        if dump:
-            cost_out = torch.empty((G, T, T), dtype=torch.float64, device=dev)
-            mats = torch.empty((G, 5, T + 1, T + 1), dtype=torch.float64, device=dev)
-            bp = torch.empty((G, 5, T + 1, T + 1), dtype=torch.int8, device=dev)
-            l_out = torch.empty((G, T + 1, T + 1), dtype=torch.float64, device=dev)
-            out.update(cost=cost_out, mats=mats, bp=bp, L=l_out)
-        trans = (c_f64 * 25)(*self.trans.reshape(-1).tolist())
-        start = (c_f64 * 3)(*self.start.tolist())
-        _lib.check(lib.g2g_cost_dp(_ptr(trends), G, T, trans, start, self.c_model, N_SAMPLES, _ptr(cost_in),
-                                   _ptr(out["align_str"]), _ptr(out["align_len"]), _ptr(out["opt_cost"]),
-                                   _ptr(out["l_states"]), _ptr(cost_out), _ptr(mats), _ptr(bp), _ptr(l_out),
-                                   _stream()), "g2g_cost_dp")
-        return out
+        return run_cost_dp(trends, self.n_bins, self.trans, self.start, self.c_model, cost_in=cost_in, dump=dump,
+                           out=out)
 
     def time_moments(self, start_event, end_event):
         """Launch K1 alone between two CUDA events on the current stream (roofline measurement;

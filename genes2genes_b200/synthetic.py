@@ -15,6 +15,9 @@ CONFIGS = {
     "C3": (994, 3157, 890, 13),
     "C4": (20000, 100000, 100000, 50),
     "C5": (30000, 1000000, 1000000, 100),
+    # one rank's gene block of C4 / C5 when sharded over 8 GPUs (C5 with the cell count cut to fit a bench host)
+    "C4_8": (2500, 100000, 100000, 50),
+    "C5_8s": (3750, 100000, 100000, 100),
 }
 
 

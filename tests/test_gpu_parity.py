@@ -357,3 +357,58 @@ def test_distributed_api_matches_single_gpu(tmp_path):
                           "--master-addr", "127.0.0.1", "--master-port", "29541", str(script)],
                          capture_output=True, text=True, timeout=600)
     assert "DIST_OK %d 203" % n in out.stdout, out.stdout[-2000:] + out.stderr[-4000:]
+
+
+def test_large_shape_properties_T50():
+    """Size-independent properties at a whole-transcriptome-like shape (T = 50, 110k cells):
+    a sample of genes equals the batched oracle; duplicated gene columns give identical records;
+    aligning a dataset against itself matches every bin (all 'M')."""
+    torch = _torch()
+    G, nr, nq, T = 768, 60000, 50000, 50
+    Xr, tr, Xq, tq, _ = synthetic.make_pair(G, nr, nq, dropout=0.9, seed=77)
+    Xr[:, 5] = Xr[:, 400]          # duplicated genes (different 32-gene tiles)
+    Xq[:, 5] = Xq[:, 400]
+    eng = _engine_from_arrays(Xr, tr, Xq, tq, T)
+    h = eng.run().results_to_host()
+    for k in h:
+        assert np.array_equal(h[k][5], h[k][400]), k
+    sel = np.r_[0:24, 400, 760:768]
+    ref = o.align_batch(np.ascontiguousarray(Xr[:, sel]), np.ascontiguousarray(Xq[:, sel]), tr, tq, T)
+    got = _strings(h)
+    for n, g in enumerate(sel):
+        assert o.canonical_gap_blocks(got[g]) == o.canonical_gap_blocks(ref["alignment_str"][n]), g
+    np.testing.assert_allclose(h["opt_cost"][sel], ref["opt_cost"], rtol=5e-5)
+    for k, key in enumerate(("mu_S", "sd_S", "mu_T", "sd_T")):
+        want = ref[key]
+        scale = np.maximum(np.abs(want), np.abs(want).max(axis=1, keepdims=True) * 1e-2) + 1e-12
+        assert (np.abs(h["musigma"][sel, k] - want) / scale).max() < RTOL_MOMENTS, key
+    del eng
+    # self alignment: identical series on both sides
+    eng = _engine_from_arrays(Xr[:, :256], tr, Xr[:, :256], tr, T)
+    h = eng.run().results_to_host()
+    expressed = (h["flags"] & 3) == 3
+    strs = _strings(h)
+    assert expressed.sum() > 200
+    assert all(s == "M" * T for s, e in zip(strs, expressed) if e)
+
+
+def test_csr_input_equals_dense_input():
+    """``g2g_pack_csr`` (sparse upload, gene subset, row order) builds the same device matrix as
+    ``g2g_pack_rows`` on the densified data."""
+    torch = _torch()
+    import scipy.sparse as sp
+    from genes2genes_b200 import engine
+    rng = np.random.default_rng(3)
+    X = (rng.uniform(size=(700, 333)) < 0.1) * rng.uniform(0.1, 5, (700, 333))
+    X = X.astype(np.float32)
+    order = rng.permutation(700)
+    genes = np.sort(rng.choice(333, 150, replace=False)).astype(np.int32)
+    dev = torch.device("cuda", 0)
+    a = engine.pack_dense(X, order, genes, dev)
+    b = engine.pack_csr(sp.csr_matrix(X), order, genes, 333, dev)
+    torch.cuda.synchronize()
+    assert a.shape == b.shape == (700, 152)
+    assert torch.equal(a, b)
+    assert np.array_equal(a.cpu().numpy()[:, :150], X[order][:, genes])
+    c = engine.pack_csr(sp.csr_matrix(X), None, None, 333, dev)
+    assert np.array_equal(c.cpu().numpy()[:, :333], X)

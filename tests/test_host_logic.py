@@ -58,44 +58,30 @@ def test_matched_points_equal_dp_cells_on_random_legal_strings():
         assert list(zip(S.tolist(), T.tolist())) == want, s
 
 
-class _FakeAligner:
-    """Just enough of RefQueryAligner for AligmentObj views: host result arrays without a GPU."""
-
-    def __init__(self, ref, T):
-        G = len(ref["alignment_str"])
-        self.gene_list = ["g%d" % k for k in range(G)]
-        self.n_artificial_time_points = T
-        self._gene_index = {g: k for k, g in enumerate(self.gene_list)}
-        self._aligned_state_params = (0.99, 0.1, 0.7)
-        self.pairs = Main._LazyPairs(self)
-        strs = [str(s).encode() for s in ref["alignment_str"]]
-        buf = np.zeros((G, 2 * T), dtype=np.uint8)
-        for g, b in enumerate(strs):
-            buf[g, :len(b)] = np.frombuffer(b, dtype=np.uint8)
-        self._host = {
-            "align_str": buf, "align_len": np.array([len(b) for b in strs], dtype=np.int32),
-            "opt_cost": ref["opt_cost"], "l_states": ref["L_states"].reshape(G, -1).astype(np.uint8),
-            "musigma": np.stack([ref["intpl_means_S"], ref["intpl_stds_S"], ref["intpl_means_T"],
-                                 ref["intpl_stds_T"]], axis=1),
-            "trends": np.stack([ref["mean_trend_S"], ref["std_trend_S"], ref["mean_trend_T"], ref["std_trend_T"]],
-                               axis=1)}
-
-        class _TI:
-            interpolation_points = np.linspace(0, 1, T)
-
-        class _Eng:
-            eps = engine.epsilon_table(T)
-
-        self.TrajInt_R = self.TrajInt_Q = _TI()
-        self._engine = _Eng()
-
-    _series_pair = Main.RefQueryAligner._series_pair
+def _store_from_reference(ref, T):
+    """A result store filled with the reference's own outputs: exercises every AligmentObj view
+    without a GPU."""
+    G = len(ref["alignment_str"])
+    strs = [str(s).encode() for s in ref["alignment_str"]]
+    buf = np.zeros((G, 2 * T), dtype=np.uint8)
+    for g, b in enumerate(strs):
+        buf[g, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    host = {
+        "align_str": buf, "align_len": np.array([len(b) for b in strs], dtype=np.int32),
+        "opt_cost": ref["opt_cost"], "l_states": ref["L_states"].reshape(G, -1).astype(np.uint8),
+        "musigma": np.stack([ref["intpl_means_S"], ref["intpl_stds_S"], ref["intpl_means_T"],
+                             ref["intpl_stds_T"]], axis=1),
+        "trends": np.stack([ref["mean_trend_S"], ref["std_trend_S"], ref["mean_trend_T"], ref["std_trend_T"]],
+                           axis=1)}
+    pts = np.linspace(0, 1, T)
+    return Main._ResultStore(host, ["g%d" % k for k in range(G)], T, engine.epsilon_table(T), pts, pts,
+                             (0.99, 0.1, 0.7), None)
 
 
 def test_aligment_obj_fields_from_reference_strings(golden_dir):
     ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
-    al = _FakeAligner(ref, 14)
-    results = [Main.AligmentObj(al, g, al.gene_list[g]) for g in range(89)]
+    store = _store_from_reference(ref, 14)
+    results = [Main.AligmentObj(store, g, store.gene_list[g]) for g in range(89)]
     for g in range(0, 89, 7):
         a = results[g]
         assert a.alignment_str == str(ref["alignment_str"][g])
