@@ -244,19 +244,37 @@ def run_b200(args):
     step()  # first run sets kernel attributes / loads modules
     torch.cuda.synchronize()
     graph = None
-    if not args.no_graph and world == 1:
-        graph = torch.cuda.CUDAGraph()
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            eng.run()
-            side.synchronize()
-            with torch.cuda.graph(graph, stream=side):
+    if not args.no_graph:
+        # the 8 kernel launches of a step replay as one CUDA graph; the NCCL gather (N > 1) stays an
+        # eager call after the replay (a captured collective hung process-group teardown on this stack)
+        try:
+            g = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
                 eng.run()
-        torch.cuda.current_stream().wait_stream(side)
+                side.synchronize()
+                with torch.cuda.graph(g, stream=side):
+                    eng.run()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = g
+        except Exception as exc:  # capture is an optimisation; fall back to eager launches
+            print("CUDA graph capture failed (%s); running eagerly" % exc, file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+
+    def timed_step():
+        if graph is not None:
+            graph.replay()
+            if gather is not None:
+                gather.run()
+        else:
+            step()
+
     for _ in range(args.warmup):
         flush_buf.fill_(1)
-        graph.replay() if graph is not None else step()
+        timed_step()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -271,10 +289,7 @@ def run_b200(args):
     for k in range(args.steps):
         flush_buf.fill_(k & 0xFF)      # evict X and the partial sums from L2 (not timed)
         starts[k].record()
-        if graph is not None:
-            graph.replay()
-        else:
-            step()
+        timed_step()
         ends[k].record()
     torch.cuda.synchronize()
     if world > 1:
@@ -359,6 +374,8 @@ def run_b200(args):
                                               % (min(args.cpu_genes, G), time.perf_counter() - t0)}
         print(json.dumps(line))
     if world > 1:
+        del graph
+        torch.cuda.synchronize()
         dist.barrier()
         dist.destroy_process_group()
 
