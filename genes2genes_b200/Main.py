@@ -604,6 +604,26 @@ class RefQueryAligner:
         self.results_map = {a.gene: a for a in self.results}
         self._say("Alignment completed! ✅")
 
+    # -- aggregate alignment (reference: Main.py:498-510) ---------------------------------------------
+    def get_aggregate_alignment(self):
+        """Cell-level average alignment over all genes; sets ``average_alignment`` and returns
+        (string, path, match-count DataFrame).  The reference also draws the path on a heat map."""
+        return self._aggregate(self.gene_list, True)
+
+    def get_aggregate_alignment_for_subset(self, gene_subset):
+        return self._aggregate(gene_subset, False)
+
+    def _aggregate(self, genes, remember):
+        from . import ClusterUtils
+        average_alignment, alignment_path = ClusterUtils.get_cluster_average_alignments(self, genes)
+        mat = ClusterUtils.get_pairwise_match_count_mat(self, genes)
+        self._say("Average Alignment: ", alignment_visual(average_alignment)[1], "(cell-level)")
+        if remember:
+            pct = np.round(len(re.findall("M|W|V", average_alignment)) * 100 / len(average_alignment), 2)
+            self._say("% similarity:", pct)
+            self.average_alignment = average_alignment
+        return average_alignment, alignment_path, mat
+
     # -- summaries ------------------------------------------------------------------------------------
     def get_match_stat_for_all_genes(self):
         import pandas as pd

@@ -6,6 +6,7 @@ Host code is Python/PyTorch over ``libg2g.so`` (hand-written sm_100a CUDA, C ABI
 ``include/g2g.h``).  There is no CPU fallback: without the built library or a CUDA device the
 aligner raises.
 """
+from . import ClusterUtils  # noqa: F401
 from . import Main  # noqa: F401
 from . import OrgAlign  # noqa: F401
 from . import TimeSeriesPreprocessor  # noqa: F401

@@ -44,6 +44,8 @@ SIGNATURES = {
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_cost_dp": (c_i32, [c_vp, c_i64, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, c_i32,
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "g2g_state_histogram": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "g2g_match_counts": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

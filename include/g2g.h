@@ -185,6 +185,21 @@ int g2g_cost_dp(const double* trends, int64_t n_genes, int32_t n_bins, const dou
                 uint8_t* align_str, int32_t* align_len, double* opt_cost, uint8_t* l_states,
                 double* cost_out, double* mats_out, int8_t* bp_out, double* l_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Aggregate (cell-level) alignment over a gene set -- SURVEY.md 8(f) row f2.
+ * g2g_state_histogram: counts[k][cell] = number of selected genes whose landscape state at DP cell
+ *   `cell` is k (M,W,V,D,I); replaces the counting loop of ClusterUtils.get_cluster_average_alignments
+ *   (ClusterUtils.py:471-490).  l_states u8 [n_genes][(n_bins+1)^2] (g2g_cost_dp output);
+ *   gene_mask u8 [n_genes] or null (= all genes); counts i32 out [5][(n_bins+1)^2].
+ * g2g_match_counts: counts[i][j] = number of selected genes that match query bin i-1 with reference
+ *   bin j-1 (M/W/V steps); replaces ClusterUtils.get_pairwise_match_count_mat (ClusterUtils.py:435-450).
+ *   counts i32 out [(n_bins+1)^2].
+ */
+int g2g_state_histogram(const uint8_t* l_states, int64_t n_genes, int32_t n_bins, const uint8_t* gene_mask,
+                        int32_t* counts, void* stream);
+int g2g_match_counts(const uint8_t* align_str, const int32_t* align_len, int64_t n_genes, int32_t n_bins,
+                     const uint8_t* gene_mask, int32_t* counts, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -108,6 +108,14 @@ def run_reference(Xr, tr, Xq, tq, genes, n_bins, adaptive=None, n_data_bins=4, a
                 "match_points_T": np.asarray(mpT), "al_visual": np.asarray(al_visual),
                 "colored": np.asarray(colored), "regions": np.asarray(regions),
                 "de_info": np.asarray(de_rows)})
+    # aggregate (cell-level) alignment and pairwise match counts over all genes
+    # (ClusterUtils.get_cluster_average_alignments / get_pairwise_match_count_mat, :435-518)
+    with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+        avg, avg_path = g2g.ClusterUtils.get_cluster_average_alignments(al, list(genes))
+        mat = g2g.ClusterUtils.get_pairwise_match_count_mat(al, list(genes))
+    out["aggregate_alignment"] = np.asarray(avg)
+    out["aggregate_path"] = np.asarray(avg_path, dtype=np.int64)
+    out["match_count_mat"] = np.asarray(mat, dtype=np.float64)
     # data_bins (bit-exactness of the epsilon table) for the first few genes, both sides
     nb = min(n_data_bins, G)
     out["data_bins_S"] = np.asarray([[np.asarray(b, dtype=np.float64) for b in al.results[g].S.data_bins]

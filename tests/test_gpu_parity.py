@@ -412,3 +412,32 @@ def test_csr_input_equals_dense_input():
     assert np.array_equal(a.cpu().numpy()[:, :150], X[order][:, genes])
     c = engine.pack_csr(sp.csr_matrix(X), None, None, 333, dev)
     assert np.array_equal(c.cpu().numpy()[:, :333], X)
+
+
+def test_aggregate_alignment_kernels(golden_dir):
+    """f2: state histogram / match-count kernels vs numpy on the same arrays, and the aggregate
+    alignment of the tutorial data vs the reference's (ClusterUtils.py:435-518)."""
+    from genes2genes_b200 import Main, ClusterUtils
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
+    inp = np.load(os.path.join(golden_dir, "tutorial_inputs.npz"))
+    genes = [str(g) for g in inp["genes"]]
+    al = Main.RefQueryAligner(AnnDataLite(inp["X_ref"], inp["time_ref"], genes),
+                              AnnDataLite(inp["X_query"], inp["time_query"], genes), genes, 14, verbose=False)
+    al.align_all_pairs()
+    h = al._store.host
+    for subset in (genes, genes[10:37]):
+        idx = [genes.index(g) for g in subset]
+        counts = ClusterUtils._device_counts(al, subset, "states")
+        L = h["l_states"][idx].reshape(len(idx), 15, 15)
+        assert np.array_equal(counts, np.stack([(L == k).sum(axis=0) for k in range(5)]))
+        mat = ClusterUtils.get_pairwise_match_count_mat(al, subset).values
+        want = np.zeros((15, 15))
+        for g in idx:
+            a = al.results[g]
+            np.add.at(want, (a.match_points_T + 1, a.match_points_S + 1), 1)
+        assert np.array_equal(mat, want)
+    s, path, mat = al.get_aggregate_alignment()
+    assert al.average_alignment == s and path[0] == [14, 14] and path[-1] == [0, 0]
+    assert o.canonical_gap_blocks(s) == o.canonical_gap_blocks(str(ref["aggregate_alignment"]))
+    assert abs(mat.values.sum() - ref["match_count_mat"].sum()) <= 4

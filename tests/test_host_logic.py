@@ -210,3 +210,22 @@ def test_shard_range_covers_all_genes():
             spans = [d.shard_range(G, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == G
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+
+
+def test_average_alignment_walk_matches_reference(golden_dir):
+    """Aggregate alignment walk fed the reference's own landscape states reproduces the reference's
+    average alignment and path (ClusterUtils.py:455-518; Tutorial.ipynb prints 47.37 %)."""
+    from genes2genes_b200 import ClusterUtils
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
+    L = ref["L_states"]
+    counts = np.stack([(L == k).sum(axis=0) for k in range(5)])
+    s, path = ClusterUtils.walk_average_alignment(counts)
+    assert s == str(ref["aggregate_alignment"])
+    assert path == ref["aggregate_path"].tolist()
+    assert round(100 * sum(c in "MWV" for c in s) / len(s), 2) == 47.37
+    # match-count matrix from matched points == the reference's
+    mat = np.zeros((15, 15))
+    for g in range(len(L)):
+        S, T = Main.matched_time_points(str(ref["alignment_str"][g]))
+        np.add.at(mat, (T + 1, S + 1), 1)
+    assert np.array_equal(mat, ref["match_count_mat"])
