@@ -441,3 +441,18 @@ def test_aggregate_alignment_kernels(golden_dir):
     assert al.average_alignment == s and path[0] == [14, 14] and path[-1] == [0, 0]
     assert o.canonical_gap_blocks(s) == o.canonical_gap_blocks(str(ref["aggregate_alignment"]))
     assert abs(mat.values.sum() - ref["match_count_mat"].sum()) <= 4
+
+
+def test_zero_variance_gene_raises_like_the_reference():
+    """A gene whose interpolated std is 0 makes the reference fail in torch's Normal validation
+    (MyFunctions.py:64); the batch reports it through flags and the API raises ValueError."""
+    from genes2genes_b200 import Main
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    G, nr, nq, T = 16, 300, 280, 10
+    Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=0.3, seed=4)
+    Xr[:, 3] = 2.5          # constant expression: weighted variance is exactly 0
+    al = Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), AnnDataLite(Xq, tq, genes), genes, T, verbose=False)
+    with pytest.raises(ValueError, match="scale"):
+        al.align_all_pairs()
+    with pytest.raises(TypeError):
+        Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), genes, T, verbose=False)
