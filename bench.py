@@ -43,6 +43,7 @@ def parse_args():
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--sparse", action="store_true", help="also report the sparse-input (CSC, work ~ nnz) variant")
     ap.add_argument("--cpu-genes", type=int, default=512, help="genes in the bounded CPU-baseline sample")
     return ap.parse_args()
 
@@ -58,7 +59,7 @@ def config_dict(name, dropout, n_gpus, extra=None):
     from genes2genes_b200 import synthetic
     G, nr, nq, T = synthetic.CONFIGS[name]
     cfg = {"workload": "%s: %d genes x (%d ref + %d query cells), %d interpolation points, dense f32 [cells x genes], "
-                       "synthetic log1p counts with %.0f%% dropout" % (name, G, nr, nq, T, dropout * 100),
+                       "synthetic log1p counts, dropout parameter %.2f (about 57%% zeros)" % (name, G, nr, nq, T, dropout),
            "genes_per_gpu": G, "n_ref_cells": nr, "n_query_cells": nq, "n_interpolation_points": T,
            "parallelism": "genes sharded over %d GPU(s), final NCCL gather to rank 0" % n_gpus if n_gpus > 1
            else "single GPU", "l2": "L2 flushed (256 MiB write) between timed steps"}
@@ -203,6 +204,66 @@ def ncu_traffic(workload_name):
         return None
 
 
+def sparse_variant(args, Xr, tr, Xq, tq, genes, T, dev, flush_buf):
+    """The same workload handed over as scipy CSR (what real single-cell matrices are): the matrix stays
+    sparse on the device (K1s, work and PCIe bytes ~ stored entries).  Reported alongside the dense
+    numbers, at the generator's own density and thinned to a typical single-cell density."""
+    import scipy.sparse as sp
+    import torch
+    from genes2genes_b200 import Main, engine
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
+    out = []
+    rng = np.random.default_rng(0)
+    for keep in (1.0, 0.25):
+        Ar = Xr if keep == 1.0 else Xr * (rng.uniform(size=Xr.shape) < keep)
+        Aq = Xq if keep == 1.0 else Xq * (rng.uniform(size=Xq.shape) < keep)
+        cr, cq = sp.csr_matrix(Ar), sp.csr_matrix(Aq)
+        density = (cr.nnz + cq.nnz) / float(Ar.size + Aq.size)
+        tir = TrajectoryInterpolator(tr, T, adaptive_kernel=False).run()
+        tiq = TrajectoryInterpolator(tq, T, adaptive_kernel=False).run()
+        eng = engine.AlignmentEngine(engine.pack_csc(cr, tir.order, None, len(genes), dev), tir.cell_pseudotimes,
+                                     engine.pack_csc(cq, tiq.order, None, len(genes), dev), tiq.cell_pseudotimes,
+                                     len(genes), T, tir.kernel_denominators(), tiq.kernel_denominators(), device=dev)
+        for _ in range(3):
+            eng.run()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
+               torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        for a, b, c, d in ev:
+            flush_buf.fill_(3)
+            a.record(); eng.run(); b.record()
+            flush_buf.fill_(4)
+            eng.time_moments(c, d)
+        torch.cuda.synchronize()
+        step_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in ev]))
+        k1_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in ev]))
+        saved = Main.RefQueryAligner.sparse_density_threshold
+        Main.RefQueryAligner.sparse_density_threshold = 1.0
+        try:
+            ar, aq = AnnDataLite(cr, tr, genes), AnnDataLite(cq, tq, genes)
+            t_e2e = []
+            for k in range(4):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                al = Main.RefQueryAligner(ar, aq, genes, T, verbose=False)
+                al.align_all_pairs()
+                n = sum(a.alignment_str.count("M") for a in al.results)
+                torch.cuda.synchronize()
+                if k:
+                    t_e2e.append(time.perf_counter() - t0)
+                del al
+        finally:
+            Main.RefQueryAligner.sparse_density_threshold = saved
+        nnz_bytes = int(cr.data.nbytes + cr.indices.nbytes + cr.indptr.nbytes + cq.data.nbytes + cq.indices.nbytes
+                        + cq.indptr.nbytes)
+        out.append({"density": density, "ms_per_step": step_ms, "value": len(genes) / (step_ms * 1e-3),
+                    "k1s_kernel_ms": k1_ms, "nnz_gather_GBps": (cr.nnz + cq.nnz) * 72 / (k1_ms * 1e-3) / 1e9,
+                    "e2e_ms": float(np.mean(t_e2e)) * 1e3, "e2e_value": len(genes) / float(np.mean(t_e2e)),
+                    "h2d_bytes_per_step": nnz_bytes, "input": "scipy CSR on the host (pageable)"})
+        del eng
+    return out
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -341,6 +402,10 @@ def run_b200(args):
         e2e_t = float(t.item())
     h2d = int(Xr.nbytes + Xq.nbytes + tr.nbytes + tq.nbytes)
 
+    sparse_report = None
+    if world == 1 and args.sparse:
+        sparse_report = sparse_variant(args, Xr, tr, Xq, tq, genes, T, dev, flush_buf)
+
     if rank == 0:
         peak, peak_src = measured_peak()
         nr, nq = Xr.shape[0], Xq.shape[0]
@@ -365,6 +430,8 @@ def run_b200(args):
                          "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / (float(np.mean(ms)))},
             "clocks": clocks,
         }
+        if sparse_report is not None:
+            line["sparse_variant"] = sparse_report
         if not args.no_cpu_baseline and world == 1:
             t0 = time.perf_counter()
             rate = cpu_port_rate(Xr, tr, Xq, tq, T, args.cpu_genes, 1)

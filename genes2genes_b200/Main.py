@@ -401,6 +401,12 @@ class RefQueryAligner:
     ``.obs['time']`` in [0, 1], ``.var_names`` and ``.obs_names``.
     """
 
+    #: scipy-sparse inputs at most this dense stay sparse on the device (K1s: work and memory ~ stored
+    #: entries; measured break-even with the dense kernel near 9 % on B200, DESIGN.md section 7); denser
+    #: ones are densified on the device and streamed by K1.  Set to 1.0 to force the sparse path when the
+    #: dense matrix would not fit in HBM.
+    sparse_density_threshold = 0.08
+
     def __init__(self, *args, device=None, verbose=True, distributed=False):
         """``distributed=True`` (inside an initialised ``torch.distributed`` job, one process per GPU):
         this rank aligns its contiguous block of ``gene_list`` and ``align_all_pairs`` gathers every
@@ -454,9 +460,21 @@ class RefQueryAligner:
         self.TrajInt_Q = TimeSeriesPreprocessor.TrajectoryInterpolator(
             self.query_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
             obs_names=getattr(adata_query, "obs_names", None)).run()
+        try:
+            import scipy.sparse as _sp
+            self._both_sparse = _sp.issparse(adata_ref.X) and _sp.issparse(adata_query.X)
+        except Exception:
+            self._both_sparse = False
         with torch.cuda.device(self.device):
             Xr = self._pack(adata_ref, self.TrajInt_R.order)
             Xq = self._pack(adata_query, self.TrajInt_Q.order)
+            if isinstance(Xr, _engine.CscMatrix) != isinstance(Xq, _engine.CscMatrix):
+                # one side fell over the density threshold: densify the sparse one too
+                self._both_sparse = False
+                if isinstance(Xr, _engine.CscMatrix):
+                    Xr = self._pack(adata_ref, self.TrajInt_R.order)
+                else:
+                    Xq = self._pack(adata_query, self.TrajInt_Q.order)
             self._engine = _engine.AlignmentEngine(
                 Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(self._local_genes),
                 self.n_artificial_time_points, self.TrajInt_R.kernel_denominators(),
@@ -488,7 +506,11 @@ class RefQueryAligner:
         except Exception:  # scipy always ships with the reference's dependencies; be permissive
             is_sparse = False
         if is_sparse:
-            return _engine.pack_csr(X.tocsr(), row_order, gene_idx, X.shape[1], self.device)
+            X = X.tocsr()
+            density = X.nnz / max(1, X.shape[0] * X.shape[1])
+            if self._both_sparse and density <= self.sparse_density_threshold:
+                return _engine.pack_csc(X, row_order, gene_idx, X.shape[1], self.device)
+            return _engine.pack_csr(X, row_order, gene_idx, X.shape[1], self.device)
         if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
             X = X.todense()
         if isinstance(X, np.matrix):

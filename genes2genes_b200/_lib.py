@@ -27,6 +27,11 @@ class Side(ctypes.Structure):
                 ("part_f64", c_vp), ("part_i32", c_vp)]
 
 
+class SparseSide(ctypes.Structure):
+    _fields_ = [("col_ptr", c_vp), ("row_idx", c_vp), ("values", c_vp), ("n_cells", c_i64), ("wtab", c_vp),
+                ("pilot", c_vp), ("part_f64", c_vp), ("part_i32", c_vp)]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against include/g2g.h
 SIGNATURES = {
     "g2g_version": (c_i32, []),
@@ -39,6 +44,7 @@ SIGNATURES = {
     "g2g_weights": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_pilot_mean": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "g2g_moments": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp]),
+    "g2g_moments_csc": (c_i32, [ctypes.POINTER(SparseSide), c_i32, c_i64, c_i64, c_i32, c_vp]),
     "g2g_fixup_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "g2g_fixup_trends": (c_i32, [ctypes.POINTER(Side), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32,
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),

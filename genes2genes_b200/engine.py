@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import Side, c_f64
+from ._lib import Side, SparseSide, c_f64
 
 N_SAMPLES = 50  # reference: generate_random_dataset(50, ...)  TimeSeriesPreprocessor.py:179
 
@@ -90,9 +90,11 @@ class DeviceSide:
     """Device-resident state of one dataset: packed expression matrix, weight table, workspaces."""
 
     def __init__(self, X, tau_sorted, n_genes, n_bins, denom, device):
-        self.X = X  # f32 [n_cells, ld] time-sorted, ld % 4 == 0
+        # X: dense f32 [n_cells, ld] (time-sorted rows, ld % 4 == 0) or a CscMatrix (gene-major sparse)
+        self.csc = X if isinstance(X, CscMatrix) else None
+        self.X = None if self.csc is not None else X
         self.n_cells = int(X.shape[0])
-        self.ld = int(X.shape[1])
+        self.ld = 0 if self.csc is not None else int(X.shape[1])
         self.n_genes = n_genes
         lay = _lib.layout(self.n_cells, n_bins)
         self.layout = lay
@@ -109,8 +111,31 @@ class DeviceSide:
         self.part_i32 = torch.empty(lay.n_split * n_bins * n_genes, dtype=torch.int32, device=device)
 
     def c_side(self):
-        return Side(self.X.data_ptr(), self.n_cells, self.ld, self.wtab.data_ptr(), self.pilot.data_ptr(),
-                    self.part_f64.data_ptr(), self.part_i32.data_ptr())
+        return Side(self.X.data_ptr() if self.X is not None else None, self.n_cells, self.ld, self.wtab.data_ptr(),
+                    self.pilot.data_ptr(), self.part_f64.data_ptr(), self.part_i32.data_ptr())
+
+    def c_sparse_side(self):
+        c = self.csc
+        return SparseSide(c.col_ptr.data_ptr(), c.row_idx.data_ptr(), c.values.data_ptr(), self.n_cells,
+                          self.wtab.data_ptr(), self.pilot.data_ptr(), self.part_f64.data_ptr(),
+                          self.part_i32.data_ptr())
+
+
+class CscMatrix:
+    """Gene-major sparse expression matrix on the device: ``col_ptr`` i64 [G+1], ``row_idx`` i32 [nnz]
+    (cell index in time-sorted order, ascending inside a column), ``values`` f32 [nnz]."""
+
+    def __init__(self, col_ptr, row_idx, values, n_cells, n_genes):
+        self.col_ptr, self.row_idx, self.values = col_ptr, row_idx, values
+        self.shape = (int(n_cells), int(n_genes))
+
+    @property
+    def nnz(self):
+        return int(self.values.numel())
+
+    @property
+    def device(self):
+        return self.values.device
 
 
 def pack_dense(X, row_order, gene_idx, device):
@@ -187,6 +212,33 @@ def run_cost_dp(trends, n_bins, trans, start, c_model, cost_in=None, dump=False,
     return out
 
 
+def pack_csc(csr, row_order, gene_idx, n_all_genes, device):
+    """scipy CSR (cells x all genes) -> time-sorted, gene-selected ``CscMatrix`` on the device.  Only the
+    stored entries cross PCIe; the transposition is a stable device sort by (gene, sorted cell)."""
+    n_cells = csr.shape[0]
+    n_genes = n_all_genes if gene_idx is None else len(gene_idx)
+    indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device, non_blocking=True)
+    cols = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int64)).to(device, non_blocking=True)
+    vals = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(device, non_blocking=True)
+    rows = torch.repeat_interleave(torch.arange(n_cells, device=device), indptr[1:] - indptr[:-1])
+    if row_order is not None:  # rank of every original row in the time-sorted order
+        rank = torch.empty(n_cells, dtype=torch.int64, device=device)
+        rank[torch.as_tensor(np.ascontiguousarray(row_order, dtype=np.int64)).to(device)] = torch.arange(
+            n_cells, device=device)
+        rows = rank[rows]
+    if gene_idx is not None:
+        cm = np.full(n_all_genes, -1, dtype=np.int64)
+        cm[np.asarray(gene_idx)] = np.arange(n_genes)
+        cols = torch.from_numpy(cm).to(device)[cols]
+        keep = cols >= 0
+        cols, rows, vals = cols[keep], rows[keep], vals[keep]
+    key, perm = torch.sort(cols * n_cells + rows)  # keys are unique: (gene, cell) pairs
+    counts = torch.bincount(cols, minlength=n_genes)
+    col_ptr = torch.zeros(n_genes + 1, dtype=torch.int64, device=device)
+    torch.cumsum(counts, 0, out=col_ptr[1:])
+    return CscMatrix(col_ptr, (key % n_cells).to(torch.int32), vals[perm].contiguous(), n_cells, n_genes)
+
+
 class AlignmentEngine:
     """Runs the whole hot path for one (reference, query) pair of packed device matrices.
 
@@ -200,6 +252,9 @@ class AlignmentEngine:
         _lib.check(self.lib.g2g_check_device(), "g2g_check_device")
         self.device = device if device is not None else X_ref.device
         self.n_genes, self.n_bins = int(n_genes), int(n_bins)
+        self.sparse = isinstance(X_ref, CscMatrix)
+        if self.sparse != isinstance(X_query, CscMatrix):
+            raise ValueError("reference and query must both be dense or both be CscMatrix")
         T, G, dev = self.n_bins, self.n_genes, self.device
         self.ref = DeviceSide(X_ref, tau_ref, G, T, denom_ref, dev)
         self.query = DeviceSide(X_query, tau_query, G, T, denom_query, dev)
@@ -221,6 +276,8 @@ class AlignmentEngine:
         self.opt_cost = torch.empty(G, **f64)
         self.l_states = torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev)
         self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
+        self._sparse_sides = (SparseSide * 2)(self.ref.c_sparse_side(), self.query.c_sparse_side()) \
+            if self.sparse else None
         self.fix_ws_bytes = self.lib.g2g_fixup_workspace_bytes(G, T)
         self.fix_ws = torch.empty((self.fix_ws_bytes + 7) // 8, **f64)
         self.launches_per_run = 0
@@ -244,16 +301,20 @@ class AlignmentEngine:
             st = ctypes.c_void_p(stream.cuda_stream)
             _lib.check(lib.g2g_weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
                                        _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
-            _lib.check(lib.g2g_pilot_mean(_ptr(s.X), s.n_cells, G, s.ld, _ptr(s.pilot), st), "g2g_pilot_mean")
+            if not self.sparse:
+                _lib.check(lib.g2g_pilot_mean(_ptr(s.X), s.n_cells, G, s.ld, _ptr(s.pilot), st), "g2g_pilot_mean")
         self._ev_join.record(self._side_stream)
         cur.wait_event(self._ev_join)
         st = _stream()
-        _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+        if self.sparse:
+            _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
+        else:
+            _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
         _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
                                         _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
                                         _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), _ptr(self.fix_ws),
                                         self.fix_ws_bytes, st), "g2g_fixup_trends")
-        return 7  # 2 x (weights, pilot) + moments + partial reduce + fix-up
+        return 5 if self.sparse else 7  # 2 x (weights[, pilot]) + moments + partial reduce + fix-up
 
     def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None, force_new=False):
         """K4 on all genes (or ``gene_slice`` / the given ``trends``).  ``dump=True`` also returns the
@@ -272,8 +333,12 @@ class AlignmentEngine:
         """Launch K1 alone between two CUDA events on the current stream (roofline measurement;
         the weight tables and pilot values of the last run are reused)."""
         start_event.record()
-        _lib.check(self.lib.g2g_moments(self._sides, 2, self.n_genes, self.n_genes, self.n_bins, _stream()),
-                   "g2g_moments")
+        if self.sparse:
+            _lib.check(self.lib.g2g_moments_csc(self._sparse_sides, 2, self.n_genes, self.n_genes, self.n_bins,
+                                                _stream()), "g2g_moments_csc")
+        else:
+            _lib.check(self.lib.g2g_moments(self._sides, 2, self.n_genes, self.n_genes, self.n_bins, _stream()),
+                       "g2g_moments")
         end_event.record()
 
     def run(self):

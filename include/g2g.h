@@ -140,6 +140,29 @@ int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64
                 int32_t n_bins, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K1s g2g_moments_csc -- sparse variant of g2g_moments: the expression matrix
+ * stays in compressed-sparse-column form (gene major), work and bytes are proportional to the number
+ * of stored entries.  Same outputs as g2g_moments with shift a = 0 (pilot[] is set to 0 by the call;
+ * do not call g2g_pilot_mean): the totals go to split 0 of part_f64 / part_i32, the other splits are
+ * zeroed, so g2g_fixup_trends is used unchanged.
+ *   col_ptr  i64 [n_genes+1]; row_idx i32 [nnz] = cell index of each entry in the order of tau / wtab
+ *   (ascending inside a column for deterministic sums); values f32 [nnz].
+ */
+typedef struct {
+  const int64_t* col_ptr;
+  const int32_t* row_idx;
+  const float* values;
+  int64_t n_cells;
+  const float* wtab;
+  float* pilot;
+  double* part_f64;
+  int32_t* part_i32;
+} g2g_sparse_side_t;
+
+int g2g_moments_csc(const g2g_sparse_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                    int32_t n_bins, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K3  g2g_fixup_trends -- per gene: finish the moments, apply the low-expression policy, make trends.
  * Replaces the arithmetic of compute_stat (TSP.py:166-177), RefQueryAligner.run_interpolation
  * (Main.py:344-406), check_inconsistent_zero_region / extract_significant_regions_only

@@ -456,3 +456,53 @@ def test_zero_variance_gene_raises_like_the_reference():
         al.align_all_pairs()
     with pytest.raises(TypeError):
         Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), genes, T, verbose=False)
+
+
+@pytest.mark.parametrize("T", [14, 50, 100])
+def test_sparse_csc_path_equals_dense_path(T):
+    """f3: the sparse (CSC, work ~ nnz) interpolation path gives the dense path's results: identical
+    integer outputs, moments within tolerance, canonical strings equal; through the engine and
+    through the public API (scipy CSR input, gene subset, unsorted cells)."""
+    import scipy.sparse as sp
+    torch = _torch()
+    from genes2genes_b200 import Main, engine
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
+    G, nr, nq = 150, 2500, 1800
+    Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=0.9, seed=31 + T)
+    rng = np.random.default_rng(T)   # thin out to a realistic single-cell density (~13 % stored entries)
+    Xr = Xr * (rng.uniform(size=Xr.shape) < 0.3)
+    Xq = Xq * (rng.uniform(size=Xq.shape) < 0.3)
+    dense = _engine_from_arrays(Xr, tr, Xq, tq, T).run().results_to_host()
+    dev = torch.device("cuda", 0)
+    tir, tiq = TrajectoryInterpolator(tr, T, False).run(), TrajectoryInterpolator(tq, T, False).run()
+    cr = engine.pack_csc(sp.csr_matrix(Xr), tir.order, None, G, dev)
+    cq = engine.pack_csc(sp.csr_matrix(Xq), tiq.order, None, G, dev)
+    assert cr.nnz == np.count_nonzero(Xr)
+    eng = engine.AlignmentEngine(cr, tir.cell_pseudotimes, cq, tiq.cell_pseudotimes, G, T,
+                                 tir.kernel_denominators(), tiq.kernel_denominators(), device=dev)
+    sparse = eng.run().results_to_host()
+    again = eng.run().results_to_host()
+    for k in sparse:
+        assert np.array_equal(sparse[k], again[k]), k          # run-to-run bitwise
+    assert np.array_equal(sparse["nnz"], dense["nnz"]) and np.array_equal(sparse["flags"], dense["flags"])
+    scale = np.maximum(np.abs(dense["musigma"]), np.abs(dense["musigma"]).max(axis=2, keepdims=True) * 1e-2) + 1e-12
+    assert (np.abs(sparse["musigma"] - dense["musigma"]) / scale).max() < RTOL_MOMENTS
+    np.testing.assert_allclose(sparse["opt_cost"], dense["opt_cost"], rtol=5e-5)
+    a, b = _strings(sparse), _strings(dense)
+    assert sum(o.canonical_gap_blocks(x) == o.canonical_gap_blocks(y) for x, y in zip(a, b)) >= G - 1
+    if T == 14:
+        sub = genes[20:90]
+        saved = Main.RefQueryAligner.sparse_density_threshold
+        Main.RefQueryAligner.sparse_density_threshold = 0.5
+        try:
+            al = Main.RefQueryAligner(AnnDataLite(sp.csr_matrix(Xr), tr, genes),
+                                      AnnDataLite(sp.csr_matrix(Xq), tq, genes), sub, T, verbose=False)
+        finally:
+            Main.RefQueryAligner.sparse_density_threshold = saved
+        assert al._engine.sparse
+        al.align_all_pairs()
+        for k, a_obj in enumerate(al.results):
+            g = 20 + k
+            assert o.canonical_gap_blocks(a_obj.alignment_str) == o.canonical_gap_blocks(b[g])
+            assert abs(a_obj.fwd_DP.opt_cost - dense["opt_cost"][g]) <= 5e-5 * abs(dense["opt_cost"][g])
