@@ -89,3 +89,68 @@ def get_pairwise_match_count_mat(aligner, gene_set):
     j-1 (reference: ClusterUtils.py:435-450)."""
     import pandas as pd
     return pd.DataFrame(_device_counts(aligner, gene_set, "matches").astype(np.float64))
+
+
+# ---------------------------------------------------------------------------------------------------
+# alignment-string distance matrices (SURVEY.md 8(f) row f4; reference: ClusterUtils.py:21-38, 361-377)
+# ---------------------------------------------------------------------------------------------------
+def _string_batch(set_of_strings, device):
+    import torch
+    strings = [s.encode("ascii") for s in set_of_strings]
+    lens = np.array([len(b) for b in strings], dtype=np.int32)
+    stride = max(1, int(lens.max()))
+    if stride > 256:
+        raise ValueError("alignment strings longer than 256 characters are not supported")
+    buf = np.zeros((len(strings), stride), dtype=np.uint8)
+    for k, b in enumerate(strings):
+        buf[k, :len(b)] = np.frombuffer(b, dtype=np.uint8)
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    return torch.from_numpy(buf).to(dev), torch.from_numpy(lens).to(dev), lens, stride, dev
+
+
+def _integer_distances(set_of_strings, metric, device=None):
+    """u16 [n, n] integer distances from the device kernels (``csrc/g2g_strdist.cu``)."""
+    import torch
+    lib = _lib.load()
+    s_d, l_d, lens, stride, dev = _string_batch(set_of_strings, device)
+    n = len(lens)
+    with torch.cuda.device(dev):
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ws_bytes = lib.g2g_strdist_workspace_bytes(n)
+        ws = torch.empty((ws_bytes + 7) // 8, dtype=torch.int64, device=dev)
+        out = torch.empty((n, n), dtype=torch.int16, device=dev)
+        if metric == "levenshtein":
+            _lib.check(lib.g2g_levenshtein_matrix(s_d.data_ptr(), l_d.data_ptr(), n, stride, out.data_ptr(),
+                                                  ws.data_ptr(), ws_bytes, st), "g2g_levenshtein_matrix")
+            norm = None
+        else:
+            first = set_of_strings[0]
+            n_bins = sum(first.count(c) for c in "MWD")
+            if any(sum(s.count(c) for c in "MWD") != n_bins or sum(s.count(c) for c in "MVI") != n_bins
+                   for s in set_of_strings):
+                raise ValueError("hamming distance needs alignments of series with equal numbers of time points")
+            _lib.check(lib.g2g_hamming_matrix(s_d.data_ptr(), l_d.data_ptr(), n, stride, n_bins, out.data_ptr(),
+                                              ws.data_ptr(), ws_bytes, st), "g2g_hamming_matrix")
+            norm = 2 * n_bins
+        return out.cpu().numpy().view(np.uint16), lens, norm
+
+
+def compute_levenshtein_dist_matrix(set_of_strings, device=None):
+    """E[i, j] = Levenshtein(s_i, s_j) / max(len(s_i), len(s_j)) (reference: ClusterUtils.py:21-29)."""
+    d, lens, _ = _integer_distances(list(set_of_strings), "levenshtein", device)
+    return d / np.maximum(lens[:, None], lens[None, :]).astype(np.float64)
+
+
+def compute_hamming_dist_matrix(set_of_strings, device=None):
+    """Hamming distance (fraction of differing bits) between the binary path encodings
+    (reference: ClusterUtils.py:31-38, 361-377)."""
+    d, _, norm = _integer_distances(list(set_of_strings), "hamming", device)
+    return d / float(norm)
+
+
+def binary_encode_alignment_path(al_str):
+    """Reference-side bits (M, W -> 1; D -> 0) then query-side bits (M, V -> 1; I -> 0)
+    (reference: ClusterUtils.py:361-377)."""
+    S = [1 if c in "MW" else 0 for c in al_str if c in "MWD"]
+    T = [1 if c in "MV" else 0 for c in al_str if c in "MVI"]
+    return np.asarray(S + T)

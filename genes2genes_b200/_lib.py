@@ -52,6 +52,9 @@ SIGNATURES = {
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "g2g_state_histogram": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "g2g_match_counts": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
+    "g2g_strdist_workspace_bytes": (c_sz, [c_i64]),
+    "g2g_levenshtein_matrix": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    "g2g_hamming_matrix": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
 }
 
 _lib = None

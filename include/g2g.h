@@ -223,6 +223,21 @@ int g2g_state_histogram(const uint8_t* l_states, int64_t n_genes, int32_t n_bins
 int g2g_match_counts(const uint8_t* align_str, const int32_t* align_len, int64_t n_genes, int32_t n_bins,
                      const uint8_t* gene_mask, int32_t* counts, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Alignment-string distance matrices for clustering -- SURVEY.md 8(f) row f4.
+ *   strs u8 [n_strings][stride] (g2g_cost_dp's align_str layout: stride = 2*n_bins), lens i32 [n_strings];
+ *   dist u16 out [n_strings][n_strings] (integer distances; divide on the host like the reference);
+ *   workspace >= g2g_strdist_workspace_bytes(n_strings) bytes, 8-byte aligned.
+ * g2g_levenshtein_matrix replaces ClusterUtils.compute_levenshtein_dist_matrix (ClusterUtils.py:21-29;
+ *   the reference then divides by max(len)); g2g_hamming_matrix replaces compute_hamming_dist_matrix
+ *   (:31-38) on the binary path encoding of binary_encode_alignment_path (:361-377), 2*n_bins bits.
+ */
+size_t g2g_strdist_workspace_bytes(int64_t n_strings);
+int g2g_levenshtein_matrix(const uint8_t* strs, const int32_t* lens, int64_t n_strings, int32_t stride,
+                           uint16_t* dist, void* workspace, size_t workspace_bytes, void* stream);
+int g2g_hamming_matrix(const uint8_t* strs, const int32_t* lens, int64_t n_strings, int32_t stride,
+                       int32_t n_bins, uint16_t* dist, void* workspace, size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -624,3 +624,47 @@ def align_gene_faithful(x_ref, x_query, tau_ref, tau_query, W_ref, W_query, eps,
                             cost=util[2])
     res.update({"S": S, "T": T, "branch": branch, "util": util})
     return res
+
+
+# --------------------------------------------------------------------------------------
+# f4: alignment-string distances (ClusterUtils.py:21-38, 361-377)
+# --------------------------------------------------------------------------------------
+def levenshtein(a, b):
+    """Plain edit distance (what ``Levenshtein.distance`` of the python-Levenshtein package returns;
+    the package is a third-party dependency of ClusterUtils.py:8,27, absent from the reference tree)."""
+    prev = list(range(len(b) + 1))
+    for i, ca in enumerate(a, 1):
+        cur = [i]
+        for j, cb in enumerate(b, 1):
+            cur.append(min(prev[j] + 1, cur[j - 1] + 1, prev[j - 1] + (ca != cb)))
+        prev = cur
+    return prev[-1]
+
+
+def levenshtein_matrix(strings):
+    """ClusterUtils.py:21-29."""
+    return np.array([[levenshtein(a, b) / max(len(a), len(b)) for b in strings] for a in strings])
+
+
+def binary_encode_alignment_path(al_str):
+    """ClusterUtils.py:361-377."""
+    S = ""
+    T = ""
+    for ch in al_str:
+        if ch == "M":
+            S += "1"; T += "1"
+        elif ch == "W":
+            S += "1"
+        elif ch == "V":
+            T += "1"
+        elif ch == "D":
+            S += "0"
+        elif ch == "I":
+            T += "0"
+    return np.asarray([int(c) for c in S + T])
+
+
+def hamming_matrix(strings):
+    """ClusterUtils.py:31-38 (scipy cdist 'hamming' = mean of mismatching positions)."""
+    enc = np.array([binary_encode_alignment_path(s) for s in strings])
+    return (enc[:, None, :] != enc[None, :, :]).mean(axis=2)

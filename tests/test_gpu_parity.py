@@ -506,3 +506,37 @@ def test_sparse_csc_path_equals_dense_path(T):
             g = 20 + k
             assert o.canonical_gap_blocks(a_obj.alignment_str) == o.canonical_gap_blocks(b[g])
             assert abs(a_obj.fwd_DP.opt_cost - dense["opt_cost"][g]) <= 5e-5 * abs(dense["opt_cost"][g])
+
+
+def test_string_distance_matrices(golden_dir):
+    """f4: Levenshtein (Myers bit-vector kernel) and Hamming distance matrices are exact: equal to the
+    oracle's dynamic programme / scipy-style Hamming on real and random alignment strings, including
+    lengths around the 64-character word boundaries."""
+    from genes2genes_b200 import ClusterUtils
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
+    strings = [str(s) for s in ref["alignment_str"]]
+    E = ClusterUtils.compute_levenshtein_dist_matrix(strings)
+    assert np.array_equal(E, o.levenshtein_matrix(strings))
+    H = ClusterUtils.compute_hamming_dist_matrix(strings)
+    assert np.array_equal(H, o.hamming_matrix(strings))
+    assert np.array_equal(ClusterUtils.binary_encode_alignment_path(strings[3]), o.binary_encode_alignment_path(strings[3]))
+    rng = np.random.default_rng(0)
+    for lo, hi in ((1, 12), (50, 70), (60, 130), (120, 200), (250, 256)):
+        rnd = ["".join(rng.choice(list("MWVDI"), size=rng.integers(lo, hi + 1))) for _ in range(40)]
+        got = ClusterUtils.compute_levenshtein_dist_matrix(rnd)
+        assert np.array_equal(got, o.levenshtein_matrix(rnd)), (lo, hi)
+    # hamming on synthetic legal alignments of equal series length (T = 50 -> 100-bit encodings)
+    T = 50
+    legal = []
+    for _ in range(30):
+        i = j = 0
+        s = ""
+        while i < T or j < T:
+            opts = [c for c, ok in (("M", i < T and j < T), ("D", j < T), ("I", i < T), ("W", j < T and i > 0),
+                                    ("V", i < T and j > 0)) if ok]
+            c = opts[rng.integers(len(opts))]
+            s += c
+            i += c in "MVI"
+            j += c in "MWD"
+        legal.append(s)
+    assert np.array_equal(ClusterUtils.compute_hamming_dist_matrix(legal), o.hamming_matrix(legal))

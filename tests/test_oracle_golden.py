@@ -142,3 +142,15 @@ def test_significant_region_quirks():
     assert o.extract_significant_regions_only([w(2), w(3)]) == []
     # non-trailing run followed by a separate trailing singleton
     assert o.extract_significant_regions_only([w(0), w(1), w(2), w(8)]) == [p[0], p[1], p[2], p[3]]
+
+
+def test_string_distances_against_scipy_and_known_values(golden_dir):
+    """f4 oracle: Hamming equals scipy's cdist on the reference's binary encoding; Levenshtein known values."""
+    from scipy.spatial import distance
+    ref = np.load(os.path.join(golden_dir, "tutorial_ref_T14.npz"))
+    strings = [str(s) for s in ref["alignment_str"]][:30]
+    enc = np.array([o.binary_encode_alignment_path(s) for s in strings])
+    assert enc.shape[1] == 28
+    assert np.allclose(o.hamming_matrix(strings), distance.cdist(enc, enc, "hamming"))
+    assert o.levenshtein("kitten", "sitting") == 3 and o.levenshtein("", "abc") == 3
+    assert o.levenshtein("MMMDDI", "MMMIDD") == 2
