@@ -260,7 +260,12 @@ class AligmentObj:
         (Main.py:791-835).  Computed with scipy on first access (the reference pays this for every
         gene inside ``align_all_pairs``)."""
         if self._de is None:
-            self._de = _de_info(self)
+            store = self._store
+            if getattr(store, "de", None) is not None and self._host is None:
+                from . import DEStats
+                self._de = DEStats.table_for_gene(store, self._gene_idx)   # batched (compute_DE_info)
+            else:
+                self._de = _de_info(self)
         return self._de
 
     # -- printing -----------------------------------------------------------------------------------
@@ -349,6 +354,7 @@ class _ResultStore:
         self.points_ref, self.points_query = points_ref, points_query
         self.state_params = tuple(state_params)
         self.device = device
+        self.de = None
         self.pairs = _LazyPairs(self)
 
     def series_pair(self, idx):
@@ -625,6 +631,16 @@ class RefQueryAligner:
         self.results = [self._make_result(k) for k in range(len(self.gene_list))]
         self.results_map = {a.gene: a for a in self.results}
         self._say("Alignment completed! ✅")
+
+    def compute_DE_info(self):
+        """Compute ``matched_region_DE_info`` of every gene in one batch (rank statistics on the GPU,
+        p-values from scipy's null distributions; reference: Main.py:791-835 per gene).  Without this
+        call each result builds its own table with scipy on first access."""
+        from . import DEStats
+        if self._store is None:
+            self._run_batch()
+        DEStats.compute_all(self._store)
+        return self._store.de
 
     # -- aggregate alignment (reference: Main.py:498-510) ---------------------------------------------
     def get_aggregate_alignment(self):

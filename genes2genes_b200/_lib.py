@@ -55,6 +55,7 @@ SIGNATURES = {
     "g2g_strdist_workspace_bytes": (c_sz, [c_i64]),
     "g2g_levenshtein_matrix": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_sz, c_vp]),
     "g2g_hamming_matrix": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_i32, c_vp, c_vp, c_sz, c_vp]),
+    "g2g_de_statistics": (c_i32, [c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_vp]),
 }
 
 _lib = None

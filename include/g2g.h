@@ -238,6 +238,20 @@ int g2g_levenshtein_matrix(const uint8_t* strs, const int32_t* lens, int64_t n_s
 int g2g_hamming_matrix(const uint8_t* strs, const int32_t* lens, int64_t n_strings, int32_t stride,
                        int32_t n_bins, uint16_t* dist, void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * g2g_de_statistics -- rank statistics behind matched_region_DE_info, SURVEY.md 8(f) row f1.
+ * Replaces the per-pair scipy.stats.wilcoxon / ks_2samp calls of
+ * DEAnalyser.get_DE_info_for_matched_regions (Main.py:819-820) up to the p-value lookup: for pair k
+ * (gene pair_gene[k], reference bin pair_s[k], query bin pair_t[k]) the two 50-sample bins are rebuilt as
+ * mean + eps * std from musigma (g2g_fixup_trends output) and eps f64 [n_bins][50], and
+ *   r_plus[k]    sum of the average ranks of |x - y| over positive differences (zeros dropped)
+ *   n_nonzero[k] number of non-zero differences;  tie_term[k] = sum over tie groups of t^3 - t
+ *   ks_h[k]      max over pooled samples of |#{x <= v} - #{y <= v}|   (KS statistic D = h / 50)
+ */
+int g2g_de_statistics(const double* musigma, const double* eps, int32_t n_bins, const int32_t* pair_gene,
+                      const int32_t* pair_s, const int32_t* pair_t, int64_t n_pairs, double* r_plus,
+                      double* tie_term, int32_t* n_nonzero, int32_t* ks_h, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

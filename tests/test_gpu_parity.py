@@ -540,3 +540,43 @@ def test_string_distance_matrices(golden_dir):
             j += c in "MWD"
         legal.append(s)
     assert np.array_equal(ClusterUtils.compute_hamming_dist_matrix(legal), o.hamming_matrix(legal))
+
+
+@pytest.mark.parametrize("name", ["tutorial_ref_T14.npz", "synthetic_sparse_ref.npz"])
+def test_batched_de_statistics_vs_reference(golden_dir, name):
+    """f1: the batched DE table (GPU rank statistics + scipy null distributions) equals the reference's
+    per-pair scipy results (Main.py:791-835), and the per-gene lazy scipy path, for every gene whose
+    string equals the reference's."""
+    from genes2genes_b200 import Main
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    ref, Xr, tr, Xq, tq = _golden_inputs(golden_dir, name)
+    T = int(ref["n_bins"])
+    genes = [str(g) for g in ref["genes"]]
+    al = Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), AnnDataLite(Xq, tq, genes), genes, T, verbose=False)
+    al.align_all_pairs()
+    lazy = {g: al.results[g].matched_region_DE_info.values.astype(float) for g in range(0, len(genes), 9)}
+    al.compute_DE_info()
+    fresh = [Main.AligmentObj(al._store, g, genes[g]) for g in range(len(genes))]
+    checked = 0
+    for g, a in enumerate(fresh):
+        got = a.matched_region_DE_info.values.astype(float)
+        if g in lazy:
+            np.testing.assert_allclose(got, lazy[g], rtol=1e-9, atol=2e-6)
+        if a.alignment_str != str(ref["alignment_str"][g]):
+            continue
+        want = np.asarray(json.loads(str(ref["de_info"][g])), dtype=float)
+        if want.size == 0:
+            assert got.shape[0] == 0
+            continue
+        assert got.shape == want.shape
+        np.testing.assert_allclose(got[:, :4], want[:, :4], rtol=1e-12)
+        # Delta = round(cost[t, s], 7): one cell of the cost matrix (tolerance RTOL_COST_E2E of the matrix
+        # scale, a few units for the tutorial data)
+        np.testing.assert_allclose(got[:, 4], want[:, 4], rtol=1e-4, atol=5e-5)
+        np.testing.assert_allclose(got[:, 5], want[:, 5], rtol=1e-4, atol=1e-6)   # l2fc
+        # p-values are rounded to 6 decimals.  Wilcoxon / KS depend on ranks only (exact null
+        # distributions); the t-test p-value carries the f32-level moment error through m1 - m2.
+        np.testing.assert_allclose(got[:, 6:8], want[:, 6:8], atol=1.5e-6)
+        np.testing.assert_allclose(got[:, 8], want[:, 8], rtol=5e-4, atol=1.5e-6)
+        checked += 1
+    assert checked > len(genes) // 2
