@@ -33,9 +33,12 @@ struct DpParams {
 
 constexpr int kWarpsPerBlock = 4;
 
+constexpr int kMaxPrecomputeBins = 45;   // cost matrix staged in shared memory up to this many bins
+
 __host__ __device__ inline size_t dp_smem_per_warp(int T) {
   size_t b = 0;
   b += (size_t)4 * T * sizeof(double);                    // query-side per-bin terms
+  if (T <= kMaxPrecomputeBins) b += (size_t)(4 * T + T * T) * sizeof(double);  // ref-side terms + cost matrix
   b += (size_t)T * T * sizeof(uint16_t);                  // packed back-pointers (5 x 3 bits)
   b += (size_t)(T + 1) * (T + 1);                         // L states
   b += (size_t)2 * T;                                     // reversed alignment string
@@ -46,10 +49,11 @@ struct Five {
   double v[5];
 };
 
+template <int LW>
 __device__ __forceinline__ Five shfl_up5(const Five& a) {
   Five r;
 #pragma unroll
-  for (int k = 0; k < 5; ++k) r.v[k] = __shfl_up_sync(0xffffffffu, a.v[k], 1);
+  for (int k = 0; k < 5; ++k) r.v[k] = __shfl_up_sync(0xffffffffu, a.v[k], 1, LW);
   return r;
 }
 
@@ -77,24 +81,47 @@ __device__ __forceinline__ void best5_gap(const Five& src, const double* tr, dou
   first_min5(src.v[0] + tr[0], src.v[1] + tr[1], src.v[2] + tr[2], src.v[3] + tr[3], src.v[4] + tr[4], best, arg);
 }
 
+// Closed form of the MML match cost (OrgAlign.py:471-503 in the four trend vectors).  Explicit
+// roundings: every kernel instantiation (and compiler version) evaluates it with the same
+// operations, so dumped costs are the costs the DP used.
+struct CostConst { double half_n, two_c, inv_4n; };
+__device__ __forceinline__ double match_cost(double t_mu, double t_var, double t_ivar, double t_ln, double s_mu,
+                                             double s_var, double s_ivar, double s_ln, const CostConst& k) {
+  const double d = __dsub_rn(t_mu, s_mu);
+  const double d2 = __dmul_rn(d, d);
+  const double a = __fma_rn(__dadd_rn(t_var, d2), s_ivar, __fma_rn(__dadd_rn(s_var, d2), t_ivar, -2.0));
+  double u = __fma_rn(k.half_n, a, -k.two_c);
+  u = __dadd_rn(__dadd_rn(u, s_ln), t_ln);
+  return __dmul_rn(u, k.inv_4n);
+}
+
 // FULL = false is the production path (cost from trends, compact outputs only); FULL = true also
 // honours cost_in and the dense dump pointers (verification, on-demand per-gene matrices).
-template <int B, bool FULL>
+// LW lanes serve one gene: 32 in general; for short series (T + 1 <= 16 / 8 columns, B = 1) a warp
+// carries 2 / 4 genes in its half / quarter segments so fewer lanes idle.
+template <int B, bool FULL, int LW>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_constant__ DpParams p) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int GPW = 32 / LW;  // genes per warp
   const int T = p.n_bins;
   const int nC = T + 1;
-  const int lane = threadIdx.x & 31;
+  const int lane = (threadIdx.x & 31) % LW;       // lane inside this gene's segment
+  const int sub = (threadIdx.x & 31) / LW;
   const int warp = threadIdx.x >> 5;
-  const long long g = (long long)blockIdx.x * kWarpsPerBlock + warp;
-  if (g >= p.n_genes) return;  // whole warp exits together; no block-level barriers below
+  const long long g_first = ((long long)blockIdx.x * kWarpsPerBlock + warp) * GPW;
+  if (g_first >= p.n_genes) return;  // whole warp exits together; no block-level barriers below
+  const bool active = g_first + sub < p.n_genes;
+  const long long g = active ? g_first + sub : g_first;   // idle segments shadow the first gene, stores masked
 
-  unsigned char* base = smem_raw + (size_t)warp * dp_smem_per_warp(T);
+  unsigned char* base = smem_raw + (size_t)(warp * GPW + sub) * dp_smem_per_warp(T);
   double* q_mu = reinterpret_cast<double*>(base);
   double* q_var = q_mu + T;
   double* q_ivar = q_var + T;
   double* q_ln = q_ivar + T;
-  uint16_t* bp = reinterpret_cast<uint16_t*>(q_ln + T);
+  const bool precompute = T <= kMaxPrecomputeBins;
+  double* r_terms = q_ln + T;                                    // [4][T] reference-side terms
+  double* cost_s = r_terms + 4 * T;                              // [T][T] match cost (query bin, ref bin)
+  uint16_t* bp = reinterpret_cast<uint16_t*>(precompute ? cost_s + (size_t)T * T : q_ln + T);
   uint8_t* ls = reinterpret_cast<uint8_t*>(bp + (size_t)T * T);
   uint8_t* sbuf = ls + (size_t)nC * nC;
 
@@ -108,7 +135,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
   double* lout = (FULL && p.l_out) ? p.l_out + (size_t)g * nC * nC : nullptr;
 
   // ---- prologue: per-bin terms of the closed-form cost -----------------------------------
-  for (int t = lane; t < T; t += 32) {
+  for (int t = lane; t < T; t += LW) {
     double mu = tr[2 * T + t], sd = tr[3 * T + t];
     q_mu[t] = mu;
     q_var[t] = sd * sd;
@@ -126,6 +153,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
     s_ivar[b] = 1.0 / (sd * sd);
     s_ln[b] = log(sd);
   }
+
+  const CostConst kc = {p.half_n, p.two_c, p.inv_4n};
+  if (precompute && !have_cost) {
+    // all lanes fill the T x T cost matrix up front: it is off the wavefront's dependent chain
+    for (int t = lane; t < T; t += LW) {
+      const double mu = tr[t], sd = tr[T + t];
+      r_terms[t] = mu;
+      r_terms[T + t] = sd * sd;
+      r_terms[2 * T + t] = 1.0 / (sd * sd);
+      r_terms[3 * T + t] = log(sd);
+    }
+    __syncwarp();
+    for (int k = lane; k < T * T; k += LW) {
+      const int qi = k / T, rj = k - qi * T;
+      cost_s[k] = match_cost(q_mu[qi], q_var[qi], q_ivar[qi], q_ln[qi], r_terms[rj], r_terms[T + rj],
+                             r_terms[2 * T + rj], r_terms[3 * T + rj], kc);
+    }
+  }
+  __syncwarp();
 
   // ---- row 0 / column 0 initial values (OrgAlign.py:272-331) --------------------------------
   // D[0][j] = (D[0][j-1] + 0.0) + (j==1 ? -ln ProbD : I_dd), sequentially from D[0][0] = 0
@@ -159,7 +205,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
 #pragma unroll
   for (int b = 0; b < B; ++b) {
     int j = lane * B + b;
-    if (j <= T) {
+    if (j <= T && active) {
       ls[j] = (j == 0) ? 0 : 3;
       if (mout) {
 #pragma unroll
@@ -179,9 +225,9 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
   double fin_best = 0.0;  // min over the five matrices at (T, T) and its state, set by the owning lane
   int fin_state = 0;
   for (int s = 0; s < n_steps; ++s) {
-    Five nbr = shfl_up5(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
+    Five nbr = shfl_up5<LW>(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
     const int i = s - lane + 1;
-    if (i >= 1 && i <= T && lane < n_lanes) {
+    if (i >= 1 && i <= T && lane < n_lanes && active) {
       const double t_mu = q_mu[i - 1], t_var = q_var[i - 1], t_ivar = q_ivar[i - 1], t_ln = q_ln[i - 1];
       Five left = nbr, diag = nbr_prev;
 #pragma unroll
@@ -206,15 +252,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
           if (have_cost) {
             c = cin[(size_t)(i - 1) * T + (j - 1)];
           } else {
-            // explicit roundings: both kernel instantiations (and every compiler version) evaluate
-            // the closed form with the same operations, so dumped costs are the costs the DP used
-            const double d = __dsub_rn(t_mu, s_mu[b]);
-            const double d2 = __dmul_rn(d, d);
-            const double a = __fma_rn(__dadd_rn(t_var, d2), s_ivar[b],
-                                      __fma_rn(__dadd_rn(s_var[b], d2), t_ivar, -2.0));
-            double u = __fma_rn(p.half_n, a, -p.two_c);
-            u = __dadd_rn(__dadd_rn(u, s_ln[b]), t_ln);
-            c = __dmul_rn(u, p.inv_4n);
+            c = precompute ? cost_s[(size_t)(i - 1) * T + (j - 1)]
+                           : match_cost(t_mu, t_var, t_ivar, t_ln, s_mu[b], s_var[b], s_ivar[b], s_ln[b], kc);
           }
           if (cout) cout[(size_t)(i - 1) * T + (j - 1)] = c;
           int am, aw, av, ad, ai;
@@ -259,7 +298,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
   // ---- traceback (OrgAlign.py:539-607) by the lane that owns column T ------------------------
   const int owner = T / B;
   int len = 0;
-  if (lane == owner) {
+  if (lane == owner && active) {
     const double best = fin_best;
     int state = fin_state;
     p.opt_cost[g] = best;
@@ -281,22 +320,25 @@ __global__ void __launch_bounds__(kWarpsPerBlock * 32) dp_kernel(const __grid_co
     }
     p.align_len[g] = len;
   }
-  len = __shfl_sync(0xffffffffu, len, owner);
+  len = __shfl_sync(0xffffffffu, len, owner, LW);
   __syncwarp();
   uint8_t* so = p.align_str + (size_t)g * 2 * T;
-  for (int k = lane; k < 2 * T; k += 32) so[k] = (k < len) ? sbuf[2 * T - len + k] : 0;
-  uint8_t* lo = p.l_states + (size_t)g * nC * nC;
-  for (int k = lane; k < nC * nC; k += 32) lo[k] = ls[k];
+  if (active) {
+    for (int k = lane; k < 2 * T; k += LW) so[k] = (k < len) ? sbuf[2 * T - len + k] : 0;
+    uint8_t* lo = p.l_states + (size_t)g * nC * nC;
+    for (int k = lane; k < nC * nC; k += LW) lo[k] = ls[k];
+  }
 }
 
-template <int B, bool FULL>
+template <int B, bool FULL, int LW>
 int launch_dp_mode(const DpParams& p, cudaStream_t stream) {
-  size_t smem = dp_smem_per_warp(p.n_bins) * kWarpsPerBlock;
+  constexpr int GPW = 32 / LW;
+  size_t smem = dp_smem_per_warp(p.n_bins) * kWarpsPerBlock * GPW;
   if (smem > 48 * 1024) {
-    G2G_CUDA_TRY(cudaFuncSetAttribute(dp_kernel<B, FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    G2G_CUDA_TRY(cudaFuncSetAttribute(dp_kernel<B, FULL, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  unsigned blocks = (unsigned)g2g_ceil_div(p.n_genes, kWarpsPerBlock);
-  dp_kernel<B, FULL><<<blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
+  unsigned blocks = (unsigned)g2g_ceil_div(p.n_genes, kWarpsPerBlock * GPW);
+  dp_kernel<B, FULL, LW><<<blocks, kWarpsPerBlock * 32, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
 }
@@ -304,7 +346,11 @@ int launch_dp_mode(const DpParams& p, cudaStream_t stream) {
 template <int B>
 int launch_dp(const DpParams& p, cudaStream_t stream) {
   const bool full = p.cost_in || p.cost_out || p.mats_out || p.bp_out || p.l_out;
-  return full ? launch_dp_mode<B, true>(p, stream) : launch_dp_mode<B, false>(p, stream);
+  if (B == 1 && !full) {  // short series: several genes per warp
+    if (p.n_bins + 1 <= 8) return launch_dp_mode<1, false, 8>(p, stream);
+    if (p.n_bins + 1 <= 16) return launch_dp_mode<1, false, 16>(p, stream);
+  }
+  return full ? launch_dp_mode<B, true, 32>(p, stream) : launch_dp_mode<B, false, 32>(p, stream);
 }
 
 }  // namespace
