@@ -7,12 +7,11 @@
 namespace {
 
 struct FixSide {
-  const double* part_f64;  // [n_split][2T+1][g_stride]
-  const int32_t* part_i32; // [n_split][T][g_stride]
+  const double* part_f64;  // [2T+1][g_stride]  sums over all splits (stage 1 output)
+  const int32_t* part_i32; // [T][g_stride]
   const float* pilot;      // [G]
   const double* sum_w;     // [T]
   long long n_cells;
-  long long n_split;
 };
 
 struct FixParams {
@@ -257,7 +256,6 @@ extern "C" int g2g_fixup_trends(const g2g_side_t* sides, const double* sum_w_ref
     p.side[s].pilot = sides[s].pilot;
     p.side[s].sum_w = s == 0 ? sum_w_ref : sum_w_query;
     p.side[s].n_cells = sides[s].n_cells;
-    p.side[s].n_split = 1;
   }
   p.points = points; p.eps_mean = eps_mean; p.eps_std = eps_std;
   p.musigma = musigma; p.trends = trends; p.nnz = nnz; p.flags = flags;
