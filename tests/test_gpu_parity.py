@@ -194,7 +194,13 @@ def test_adaptive_kernel_vs_reference_golden(golden_dir):
 
 
 @pytest.mark.parametrize("shape", [
+    (1371, 20327, 17176, 14, 0.9),  # BASELINE.json configs[1] full size (the bench workload)
+    (89, 179, 290, 14, 0.6),        # BASELINE.json configs[0] shape
     (994, 3157, 890, 13, 0.9),      # BASELINE.json configs[2] full size
+    (48, 900, 700, 128, 0.7),       # largest supported n_bins: three bin groups, 5 DP columns per lane
+    (40, 800, 650, 29, 0.7),        # first size with one gene per thread in K1
+    (40, 800, 650, 28, 0.7),        # last size with two genes per thread
+    (40, 400, 300, 7, 0.5),         # four genes per warp in K4
     (300, 5000, 4000, 50, 0.9),     # 2 DP columns per lane, 1 gene per thread in K1
     (70, 1500, 1100, 100, 0.6),     # 4 DP columns per lane, two bin groups in K1
     (33, 700, 650, 57, 0.6),        # two bin groups of 29
