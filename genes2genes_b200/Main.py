@@ -165,15 +165,19 @@ class AligmentObj:
         "match_percentage_T": "compute_series_match_percentage",
     }
 
+    # class-level defaults keep per-object construction to four attribute writes
+    bwd_DP = None
+    _host = None
+    _visual = None
+    _points = None
+    _de = None
+
     def __init__(self, store, gene_idx, gene, host=None):
         self._store = store
         self._gene_idx = gene_idx
-        self._host = host
         self.gene = gene
-        self.bwd_DP = None
-        self._visual = None
-        self._points = None
-        self._de = None
+        if host is not None:
+            self._host = host
 
     def __getattr__(self, name):
         loader = AligmentObj._LAZY.get(name)
@@ -459,6 +463,10 @@ class RefQueryAligner:
         self.state_params = [0.99, 0.1, 0.7]  # same defaults as the reference (Main.py:218)
         self.no_extreme_cases = False
 
+        # start the host->device copies of the expression matrices first: the pseudotime sort and the
+        # kernel-width computation below run on the host while the DMA engine streams them
+        with torch.cuda.device(self.device):
+            raw_ref, raw_query = self._upload(adata_ref), self._upload(adata_query)
         k = 1
         self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
             self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
@@ -472,13 +480,14 @@ class RefQueryAligner:
         except Exception:
             self._both_sparse = False
         with torch.cuda.device(self.device):
-            Xr = self._pack(adata_ref, self.TrajInt_R.order)
-            Xq = self._pack(adata_query, self.TrajInt_Q.order)
+            Xr = self._pack(adata_ref, self.TrajInt_R.order, raw_ref)
+            Xq = self._pack(adata_query, self.TrajInt_Q.order, raw_query)
+            del raw_ref, raw_query
             if isinstance(Xr, _engine.CscMatrix) != isinstance(Xq, _engine.CscMatrix):
                 # one side fell over the density threshold: densify the sparse one too
                 self._both_sparse = False
                 if isinstance(Xr, _engine.CscMatrix):
-                    Xr = self._pack(adata_ref, self.TrajInt_R.order)
+                    Xr = self._pack(adata_ref, self.TrajInt_R.order, raw_ref)
                 else:
                     Xq = self._pack(adata_query, self.TrajInt_Q.order)
             self._engine = _engine.AlignmentEngine(
@@ -495,8 +504,30 @@ class RefQueryAligner:
             print(*a)
 
     # -- input packing ------------------------------------------------------------------------------
-    def _pack(self, adata, order):
-        """``adata[order][:, gene_list].X`` as a packed f32 device matrix."""
+    def _upload(self, adata):
+        """Asynchronous device copy of a dense ``adata.X`` (None for sparse inputs, which are uploaded
+        in compressed form by ``_pack``)."""
+        import torch
+        X = adata.X
+        try:
+            import scipy.sparse as sp
+            if sp.issparse(X):
+                return None
+        except Exception:
+            pass
+        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
+            X = X.todense()
+        if isinstance(X, np.matrix):
+            X = np.asarray(X)
+        if not torch.is_tensor(X):
+            X = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32))
+        if X.dtype != torch.float32:
+            X = X.to(torch.float32)
+        return X.to(self.device, non_blocking=True)
+
+    def _pack(self, adata, order, raw=None):
+        """``adata[order][:, gene_list].X`` as a packed f32 device matrix (``raw``: the device copy of
+        a dense ``adata.X`` started by ``_upload``)."""
         var_names = [str(v) for v in adata.var_names]
         if list(self._local_genes) == var_names:
             gene_idx = None
@@ -517,11 +548,9 @@ class RefQueryAligner:
             if self._both_sparse and density <= self.sparse_density_threshold:
                 return _engine.pack_csc(X, row_order, gene_idx, X.shape[1], self.device)
             return _engine.pack_csr(X, row_order, gene_idx, X.shape[1], self.device)
-        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
-            X = X.todense()
-        if isinstance(X, np.matrix):
-            X = np.asarray(X)
-        return _engine.pack_dense(X, row_order, gene_idx, self.device)
+        if raw is None:
+            raw = self._upload(adata)
+        return _engine.pack_dense(raw, row_order, gene_idx, self.device)
 
     @property
     def ref_mat(self):

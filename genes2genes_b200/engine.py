@@ -86,10 +86,32 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def upload_small(arrays, device):
+    """Several small host arrays -> device tensors with ONE asynchronous copy (a pageable source would
+    make every ``.to(device)`` a blocking call queued behind the big matrix upload).  ``arrays`` maps
+    name -> numpy array; 8-byte aligned slots in one pinned staging buffer."""
+    specs, total = [], 0
+    for name, a in arrays.items():
+        a = np.ascontiguousarray(a)
+        specs.append((name, a, total))
+        total += (a.nbytes + 7) // 8 * 8
+    stage = _pinned_buffer(max(total, 8))   # waits (normally not at all) for the buffer's previous copy
+    host = stage.numpy()
+    for name, a, off in specs:
+        host[off:off + a.nbytes] = a.view(np.uint8).reshape(-1)
+    dev_buf = torch.empty(max(total, 8), dtype=torch.uint8, device=device)
+    dev_buf.copy_(stage[:max(total, 8)], non_blocking=True)
+    _mark_in_flight(stage)   # the next user of this staging buffer waits for the copy to leave the host
+    out = {}
+    for name, a, off in specs:
+        out[name] = dev_buf[off:off + a.nbytes].view(_TORCH_DTYPES[a.dtype.type]).reshape(a.shape)
+    return out
+
+
 class DeviceSide:
     """Device-resident state of one dataset: packed expression matrix, weight table, workspaces."""
 
-    def __init__(self, X, tau_sorted, n_genes, n_bins, denom, device):
+    def __init__(self, X, tau_dev, n_genes, n_bins, denom_dev, device):
         # X: dense f32 [n_cells, ld] (time-sorted rows, ld % 4 == 0) or a CscMatrix (gene-major sparse)
         self.csc = X if isinstance(X, CscMatrix) else None
         self.X = None if self.csc is not None else X
@@ -98,8 +120,8 @@ class DeviceSide:
         self.n_genes = n_genes
         lay = _lib.layout(self.n_cells, n_bins)
         self.layout = lay
-        self.tau = torch.as_tensor(np.ascontiguousarray(tau_sorted, dtype=np.float64)).to(device)
-        self.denom = torch.as_tensor(np.ascontiguousarray(denom, dtype=np.float64)).to(device)
+        self.tau = tau_dev
+        self.denom = denom_dev
         self.wtab = torch.empty(lay.n_groups * lay.n_pad * lay.row_floats, dtype=torch.float32, device=device)
         self.sum_w = torch.empty(n_bins, dtype=torch.float64, device=device)
         ws = _lib.load().g2g_weights_workspace_bytes(self.n_cells, n_bins)
@@ -154,8 +176,13 @@ def pack_dense(X, row_order, gene_idx, device):
     if identity_rows and gene_idx is None and ld == ld_src:
         return Xd
     out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
-    ro = None if identity_rows else torch.as_tensor(np.ascontiguousarray(row_order, dtype=np.int64)).to(device)
-    gi = None if gene_idx is None else torch.as_tensor(np.ascontiguousarray(gene_idx, dtype=np.int32)).to(device)
+    small = {}
+    if not identity_rows:
+        small["ro"] = np.asarray(row_order, dtype=np.int64)
+    if gene_idx is not None:
+        small["gi"] = np.asarray(gene_idx, dtype=np.int32)
+    small = upload_small(small, device) if small else {}
+    ro, gi = small.get("ro"), small.get("gi")
     _lib.check(lib.g2g_pack_rows(_ptr(Xd), n_cells, n_genes, ld_src, _ptr(ro), _ptr(gi), _ptr(out), ld, _stream()),
                "g2g_pack_rows")
     return out
@@ -256,14 +283,17 @@ class AlignmentEngine:
         if self.sparse != isinstance(X_query, CscMatrix):
             raise ValueError("reference and query must both be dense or both be CscMatrix")
         T, G, dev = self.n_bins, self.n_genes, self.device
-        self.ref = DeviceSide(X_ref, tau_ref, G, T, denom_ref, dev)
-        self.query = DeviceSide(X_query, tau_query, G, T, denom_query, dev)
         self.points_host = np.linspace(0, 1, T)  # TimeSeriesPreprocessor.py:23
         self.eps = epsilon_table(T)
         f64 = dict(dtype=torch.float64, device=dev)
-        self.points = torch.as_tensor(self.points_host).to(dev)
-        self.eps_mean = torch.as_tensor(self.eps.mean(axis=1)).to(dev)
-        self.eps_std = torch.as_tensor(self.eps.std(axis=1)).to(dev)
+        small = upload_small({
+            "tau_ref": np.asarray(tau_ref, dtype=np.float64), "tau_query": np.asarray(tau_query, dtype=np.float64),
+            "denom_ref": np.asarray(denom_ref, dtype=np.float64),
+            "denom_query": np.asarray(denom_query, dtype=np.float64), "points": self.points_host,
+            "eps_mean": self.eps.mean(axis=1), "eps_std": self.eps.std(axis=1)}, dev)
+        self.ref = DeviceSide(X_ref, small["tau_ref"], G, T, small["denom_ref"], dev)
+        self.query = DeviceSide(X_query, small["tau_query"], G, T, small["denom_query"], dev)
+        self.points, self.eps_mean, self.eps_std = small["points"], small["eps_mean"], small["eps_std"]
         self.set_state_params(free_params)
         self.start = start_costs()
         self.c_model = model_constant()
@@ -368,18 +398,33 @@ class AlignmentEngine:
         return host
 
 
-_PINNED = {}
+_PINNED = {}      # n_bytes -> [pinned buffer, event of the last copy that read or wrote it]
 
 
 def _pinned_buffer(n_bytes):
-    """Pinned staging buffers are expensive to create (cudaHostAlloc); keep one per size."""
-    buf = _PINNED.get(n_bytes)
-    if buf is None:
-        if len(_PINNED) > 8:
+    """Pinned staging buffers are expensive to create (cudaHostAlloc); keep one per size.  A buffer
+    that still has a copy in flight is waited for before it is handed out again."""
+    entry = _PINNED.get(n_bytes)
+    if entry is None:
+        if len(_PINNED) > 16:
+            for _, ev in _PINNED.values():
+                if ev is not None:
+                    ev.synchronize()
             _PINNED.clear()
-        buf = torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True)
-        _PINNED[n_bytes] = buf
-    return buf
+        entry = [torch.empty(n_bytes, dtype=torch.uint8, pin_memory=True), None]
+        _PINNED[n_bytes] = entry
+    if entry[1] is not None:
+        entry[1].synchronize()
+        entry[1] = None
+    return entry[0]
+
+
+def _mark_in_flight(buf):
+    ev = torch.cuda.Event()
+    ev.record()
+    _PINNED[buf.numel()][1] = ev
 
 
 _NP_DTYPES = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}
+_TORCH_DTYPES = {np.float64: torch.float64, np.float32: torch.float32, np.int64: torch.int64, np.int32: torch.int32,
+                 np.uint8: torch.uint8}
