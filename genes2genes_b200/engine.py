@@ -313,8 +313,10 @@ class AlignmentEngine:
         self.launches_per_run = 0
         self._host_buf = None
         self._side_stream = torch.cuda.Stream(device=dev)
+        self._side_stream2 = torch.cuda.Stream(device=dev)
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
+        self._ev_join2 = torch.cuda.Event()
 
     def set_state_params(self, free_params):
         self.free_params = tuple(float(v) for v in free_params)
@@ -324,17 +326,22 @@ class AlignmentEngine:
     def run_interpolation(self):
         lib, T, G = self.lib, self.n_bins, self.n_genes
         cur = torch.cuda.current_stream()
-        # the two datasets' weight tables / pilot means are independent: fork the query side
+        # four independent small kernels: the weight tables of the two datasets go to two forked streams,
+        # the pilot means stay on the current one
         self._ev_fork.record(cur)
-        self._side_stream.wait_event(self._ev_fork)
-        for s, stream in ((self.query, self._side_stream), (self.ref, cur)):
+        for s, stream in ((self.query, self._side_stream), (self.ref, self._side_stream2)):
+            stream.wait_event(self._ev_fork)
             st = ctypes.c_void_p(stream.cuda_stream)
             _lib.check(lib.g2g_weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
                                        _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
-            if not self.sparse:
+        if not self.sparse:
+            st = _stream()
+            for s in (self.ref, self.query):
                 _lib.check(lib.g2g_pilot_mean(_ptr(s.X), s.n_cells, G, s.ld, _ptr(s.pilot), st), "g2g_pilot_mean")
         self._ev_join.record(self._side_stream)
+        self._ev_join2.record(self._side_stream2)
         cur.wait_event(self._ev_join)
+        cur.wait_event(self._ev_join2)
         st = _stream()
         if self.sparse:
             _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
