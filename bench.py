@@ -427,7 +427,13 @@ def run_b200(args):
             "roofline": {"kernel": "moments_kernel (K1 g2g_moments)", "bound": "hbm", "achieved": achieved,
                          "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / (float(np.mean(ms)))},
+                         "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / (float(np.mean(ms))),
+                         # informational: the kernel is FP32-FMA bound before it is HBM bound
+                         "compute": {"flops_per_launch": 2.0 * (2 * T + 1) * (nr + nq) * G,
+                                     "achieved_tflops": 2.0 * (2 * T + 1) * (nr + nq) * G / k1 / 1e12,
+                                     "peak_tflops": 57.2, "frac": 2.0 * (2 * T + 1) * (nr + nq) * G / k1 / 1e12 / 57.2,
+                                     "peak_source": "FFMA2 issue-rate micro-benchmark on this pool's B200 "
+                                                    "(profiles/r01_fma_peak_microbench.txt; plain FFMA: 66.4)"}},
             "clocks": clocks,
         }
         if sparse_report is not None:
