@@ -27,6 +27,12 @@ void g2g_set_error(const char* fmt, ...);
 static inline int64_t g2g_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int64_t g2g_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
 
+// Window-id slot of a weight-table row: the window k (p_k <= tau < p_{k+1}), -1 for padding rows;
+// K0 adds G2G_WIN_MIXED when the aligned group of G2G_WIN_GROUP cells the row belongs to (one warp's
+// share of a K1 stage) spans more than one window.
+#define G2G_WIN_GROUP 8
+#define G2G_WIN_MIXED 0x10000
+
 // Bin tiling shared by K0 (table layout) and K1 (register tile): see g2g_layout_t.
 struct G2GTiling {
   int n_groups, bins_per_group, bins_even, row_floats, genes_per_thread;

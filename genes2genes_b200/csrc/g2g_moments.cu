@@ -24,6 +24,7 @@ constexpr int kConsumerWarps = 8;
 constexpr int kThreads = kConsumerWarps * 32;
 constexpr int kCellTile = G2G_CELL_TILE;              // rows per stage
 constexpr int kCellsPerWarp = kCellTile / kConsumerWarps;
+static_assert(kCellsPerWarp == G2G_WIN_GROUP, "K0 flags mixed-window groups per warp share of a stage");
 constexpr int kFlushStages = 16;                       // f32 run length per thread = 16 stages * 8 cells = 128 cells
 constexpr int kMaxSides = 2;
 
@@ -127,6 +128,9 @@ __device__ __forceinline__ Item decode_item(const MomParams& p, int item) {
 __device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned long long w2, float x) {
   asm("{\n.reg .b64 xx;\nmov.b64 xx, {%2, %2};\nfma.rn.f32x2 %0, %1, xx, %0;\n}" : "+l"(acc) : "l"(w2), "f"(x));
 }
+// 1 where x != 0 (NaN counts as non-zero, like np.count_nonzero), else 0, in one FMNMX: the bit
+// pattern of min(|x|, smallest denormal) is the integer 0 or 1 (f32 denormals are not flushed here)
+__device__ __forceinline__ int nonzero_flag(float x) { return __float_as_int(fminf(fabsf(x), __int_as_float(1))); }
 __device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
@@ -258,16 +262,30 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
     }
   };
 
+  // pilot (shift) values of the item after the current one are fetched one item ahead
+  auto load_pilot = [&](int item_i, float* dst) {
+    if (item_i < p.n_items) {
+      const Item nx = decode_item(p, item_i);
+#pragma unroll
+      for (int x = 0; x < GX; ++x) {
+        long long g = (long long)nx.gt * C::GT + lane * GX + x;
+        dst[x] = g < p.n_genes ? p.side[nx.side].pilot[g] : 0.0f;
+      }
+    }
+  };
+  float a_next[GX];
+#pragma unroll
+  for (int x = 0; x < GX; ++x) a_next[x] = 0.0f;
+  load_pilot(blockIdx.x, a_next);
+
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     const Item it = decode_item(p, item);
     const MomSide& s = p.side[it.side];
     const bool do_counts = (it.bg == 0);
     float a[GX];
 #pragma unroll
-    for (int x = 0; x < GX; ++x) {
-      long long g = (long long)it.gt * C::GT + lane * GX + x;
-      a[x] = g < p.n_genes ? s.pilot[g] : 0.0f;
-    }
+    for (int x = 0; x < GX; ++x) a[x] = a_next[x];
+    load_pilot(item + gridDim.x, a_next);
     int cur_win = -1;     // window the running counts `cnt` belong to
     int since_flush = 0;
     auto flush_counts = [&]() {
@@ -284,13 +302,12 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       const float* xt = reinterpret_cast<const float*>(stage_base + (size_t)slot * C::STAGE_BYTES);
       const float* wt = xt + kCellTile * C::GT;
       const int cell0 = warp * kCellsPerWarp;
-      // counts: branch-free while all of this warp's cells share one window (time-sorted input),
-      // per-cell bookkeeping otherwise
-      int tile_cnt[GX];
-#pragma unroll
-      for (int x = 0; x < GX; ++x) tile_cnt[x] = 0;
+      // counts: K0 marks the 8-cell groups whose cells do not all lie in one window (with
+      // time-sorted input only the few groups on a window boundary); everywhere else the loop
+      // below counts straight into `cnt` for that window
       const int win0 = __float_as_int(wt[cell0 * C::RF + TBE + 1]);
-      int win_diff = 0;
+      const bool mixed = win0 >= G2G_WIN_MIXED / 2;  // warp-uniform
+      if (do_counts && !mixed && win0 != cur_win) { flush_counts(); cur_win = win0; }
 #pragma unroll(kCellUnroll)
       for (int cc = 0; cc < kCellsPerWarp; ++cc) {
         const int cell = cell0 + cc;
@@ -310,7 +327,6 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
           xv[0] = xt[cell * C::GT + lane];
         }
         const float valid = lo_f(w2[NP]);
-        win_diff |= __float_as_int(hi_f(w2[NP])) ^ win0;
 #pragma unroll
         for (int x = 0; x < GX; ++x) {
           const float d = xv[x] - a[x];
@@ -321,22 +337,21 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
             ffma2_bcast(accB[x][k], w2[k], y);
           }
           accC[x] = fmaf(valid, d, accC[x]);
-          tile_cnt[x] += (xv[x] != 0.0f) ? 1 : 0;
+          cnt[x] += nonzero_flag(xv[x]);
         }
       }
-      if (do_counts) {
-        if (win_diff == 0) {  // warp-uniform
-          if (win0 != cur_win) { flush_counts(); cur_win = win0; }
+      if (do_counts && mixed) {  // rare: take the loop's counts back, then count cell by cell
+        for (int cc = 0; cc < kCellsPerWarp; ++cc) {
 #pragma unroll
-          for (int x = 0; x < GX; ++x) cnt[x] += tile_cnt[x];
-        } else {
-          for (int cc = 0; cc < kCellsPerWarp; ++cc) {
-            const int cell = cell0 + cc;
-            const int win = __float_as_int(wt[cell * C::RF + TBE + 1]);
-            if (win != cur_win) { flush_counts(); cur_win = win; }
+          for (int x = 0; x < GX; ++x) cnt[x] -= nonzero_flag(xt[(cell0 + cc) * C::GT + lane * GX + x]);
+        }
+        for (int cc = 0; cc < kCellsPerWarp; ++cc) {
+          const int cell = cell0 + cc;
+          int win = __float_as_int(wt[cell * C::RF + TBE + 1]);
+          if (win >= G2G_WIN_MIXED / 2) win -= G2G_WIN_MIXED;
+          if (win != cur_win) { flush_counts(); cur_win = win; }
 #pragma unroll
-            for (int x = 0; x < GX; ++x) cnt[x] += (xt[cell * C::GT + lane * GX + x] != 0.0f) ? 1 : 0;
-          }
+          for (int x = 0; x < GX; ++x) cnt[x] += nonzero_flag(xt[cell * C::GT + lane * GX + x]);
         }
       }
       __syncwarp();

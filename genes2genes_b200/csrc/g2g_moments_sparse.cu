@@ -72,7 +72,8 @@ __global__ void __launch_bounds__(kSpThreads) moments_csc_kernel(const SpParams 
     }
     sx += x;
     if (x != 0.0f) {  // explicit zeros may be stored; they are not "non-zero" (np.count_nonzero)
-      const int win = __float_as_int(w[TBE + 1]);
+      int win = __float_as_int(w[TBE + 1]);
+      if (win >= G2G_WIN_MIXED / 2) win -= G2G_WIN_MIXED;
       if (win != cur_win) {
         if (cnt && cur_win >= 0) atomicAdd(&s_cnt[cur_win], cnt);
         cur_win = win;

@@ -73,6 +73,10 @@ __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams 
             for (int k = 0; k + 1 < T; ++k)
               if (tau >= s_pts[k] && tau < s_pts[k + 1]) win = k;
           }
+          // all 32 lanes (consecutive cells) are here together: b depends on the warp only
+          const unsigned same = __match_any_sync(0xffffffffu, win);
+          const unsigned group = 0xffu << ((threadIdx.x & 31) & ~(G2G_WIN_GROUP - 1));
+          if ((same & group) != group) win += G2G_WIN_MIXED;
           out = __int_as_float(win);
         }
         row[b] = out;
