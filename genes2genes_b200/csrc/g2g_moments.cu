@@ -131,6 +131,19 @@ __device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned lo
 // 1 where x != 0 (NaN counts as non-zero, like np.count_nonzero), else 0, in one FMNMX: the bit
 // pattern of min(|x|, smallest denormal) is the integer 0 or 1 (f32 denormals are not flushed here)
 __device__ __forceinline__ int nonzero_flag(float x) { return __float_as_int(fminf(fabsf(x), __int_as_float(1))); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
 __device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
 __device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
 
@@ -192,6 +205,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
   // ---- register tile: GX genes x TBE bins x {A, B} as packed f32 pairs, plus C per gene ----------
   unsigned long long accA[GX][NP], accB[GX][NP];
   float accC[GX];
+  unsigned long long accC2 = 0ull;   // GX == 2: C of both genes as one packed accumulator
   int cnt[GX];
 #pragma unroll
   for (int x = 0; x < GX; ++x) {
@@ -229,7 +243,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       }
       if (2 * TBE >= r0 && 2 * TBE < r0 + C::kRows) {
 #pragma unroll
-        for (int x = 0; x < GX; ++x) mine[(2 * TBE - r0) * C::GT + x] = accC[x];
+        for (int x = 0; x < GX; ++x)
+          mine[(2 * TBE - r0) * C::GT + x] = GX == 2 ? (x == 0 ? lo_f(accC2) : hi_f(accC2)) : accC[x];
       }
       __syncthreads();
       const int n_slots = ((C::NQ - r0 < C::kRows) ? (C::NQ - r0) : C::kRows) * C::GT;
@@ -254,6 +269,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       }
       __syncthreads();
     }
+    accC2 = 0ull;
 #pragma unroll
     for (int x = 0; x < GX; ++x) {
       accC[x] = 0.0f;
@@ -286,6 +302,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
 #pragma unroll
     for (int x = 0; x < GX; ++x) a[x] = a_next[x];
     load_pilot(item + gridDim.x, a_next);
+    const unsigned long long neg_a2 = pack2(-a[0], -a[GX - 1]);
     int cur_win = -1;     // window the running counts `cnt` belong to
     int since_flush = 0;
     auto flush_counts = [&]() {
@@ -319,25 +336,34 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
           w2[2 * q] = v.x;
           w2[2 * q + 1] = v.y;
         }
-        float xv[GX];
-        if constexpr (GX == 2) {
-          float2 v = *reinterpret_cast<const float2*>(xt + cell * C::GT + lane * 2);
-          xv[0] = v.x; xv[1] = v.y;
-        } else {
-          xv[0] = xt[cell * C::GT + lane];
-        }
         const float valid = lo_f(w2[NP]);
+        if constexpr (GX == 2) {
+          // the two genes of a lane side by side: d, y and C as packed f32x2 operations
+          const unsigned long long x2 = *reinterpret_cast<const unsigned long long*>(xt + cell * C::GT + lane * 2);
+          const unsigned long long d2 = add2(x2, neg_a2);
+          const unsigned long long y2 = mul2(d2, d2);
+          const float xs[2] = {lo_f(x2), hi_f(x2)}, ys[2] = {lo_f(y2), hi_f(y2)};
 #pragma unroll
-        for (int x = 0; x < GX; ++x) {
-          const float d = xv[x] - a[x];
+          for (int x = 0; x < 2; ++x) {
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+              ffma2_bcast(accA[x][k], w2[k], xs[x]);
+              ffma2_bcast(accB[x][k], w2[k], ys[x]);
+            }
+            cnt[x] += nonzero_flag(xs[x]);
+          }
+          ffma2_bcast(accC2, d2, valid);
+        } else {
+          const float xv = xt[cell * C::GT + lane];
+          const float d = xv - a[0];
           const float y = d * d;
 #pragma unroll
           for (int k = 0; k < NP; ++k) {
-            ffma2_bcast(accA[x][k], w2[k], xv[x]);
-            ffma2_bcast(accB[x][k], w2[k], y);
+            ffma2_bcast(accA[0][k], w2[k], xv);
+            ffma2_bcast(accB[0][k], w2[k], y);
           }
-          accC[x] = fmaf(valid, d, accC[x]);
-          cnt[x] += nonzero_flag(xv[x]);
+          accC[0] = fmaf(valid, d, accC[0]);
+          cnt[0] += nonzero_flag(xv);
         }
       }
       if (do_counts && mixed) {  // rare: take the loop's counts back, then count cell by cell
