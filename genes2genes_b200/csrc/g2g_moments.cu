@@ -27,6 +27,7 @@ constexpr int kCellsPerWarp = kCellTile / kConsumerWarps;
 static_assert(kCellsPerWarp == G2G_WIN_GROUP, "K0 flags mixed-window groups per warp share of a stage");
 constexpr int kFlushStages = 16;                       // f32 run length per thread = 16 stages * 8 cells = 128 cells
 constexpr int kMaxSides = 2;
+enum { kCurItem, kCurSide, kCurTilesLeft, kCurGene0, kCurRow, kCurGroup, kCursorInts };
 
 struct MomSide {
   const float* wtab;     // [n_groups][n_pad][RF]
@@ -50,6 +51,11 @@ struct MomParams {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ int smem_atomic_inc(int* addr) {  // called by one lane: no warp-aggregation code
+  int old;
+  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(addr)) : "memory");
+  return old;
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
   int* cnt_s = reinterpret_cast<int*>(acc64 + C::NQ * C::GT);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(cnt_s + (size_t)p.n_bins * C::GT);
   int* done = reinterpret_cast<int*>(full_bar + n_stages);  // warps finished with each stage
-  int* cursor = done + n_stages;                             // {next item, next tile} to load
+  int* cursor = done + n_stages;                             // decoded position of the next tile to load
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tid = threadIdx.x;
@@ -171,8 +177,6 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       mbar_init(&full_bar[s], 1);
       done[s] = 0;
     }
-    cursor[0] = blockIdx.x;
-    cursor[1] = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int k = tid; k < C::NQ * C::GT; k += kThreads) acc64[k] = 0.0;
@@ -180,23 +184,37 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
   __syncthreads();
 
   // Load the next tile of this CTA's item sequence into `slot`.  Only one thread runs this at a
-  // time: the prologue, then whichever warp finished the previous occupant of the slot last.
-  auto issue_next = [&](int slot_i) {
-    const int item = cursor[0];
+  // time: the prologue, then whichever warp finished the previous occupant of the slot last.  The
+  // cursor in shared memory holds the decoded position so that the common case is a few adds.
+  auto cursor_set_item = [&](int item) {
+    cursor[kCurItem] = item;
     if (item >= p.n_items) return;
-    const int tile = cursor[1];
     const Item it = decode_item(p, item);
-    const MomSide& s = p.side[it.side];
-    const float* wsrc = s.wtab + ((size_t)it.bg * s.n_pad + (size_t)it.row0 + (size_t)tile * kCellTile) * C::RF;
+    cursor[kCurSide] = it.side;
+    cursor[kCurTilesLeft] = it.n_tiles;
+    cursor[kCurGene0] = it.gt * C::GT;
+    cursor[kCurRow] = (int)it.row0;
+    cursor[kCurGroup] = it.bg;
+  };
+  auto issue_next = [&](int slot_i) {
+    if (cursor[kCurItem] >= p.n_items) return;
+    const int side = cursor[kCurSide], row = cursor[kCurRow];
+    const MomSide& s = p.side[side];
     unsigned char* dst = stage_base + (size_t)slot_i * C::STAGE_BYTES;
     mbar_arrive_expect_tx(&full_bar[slot_i], C::STAGE_BYTES);
-    tma_load_2d(dst, &p.tmap[it.side], it.gt * C::GT, (int)(it.row0 + (long long)tile * kCellTile),
-                &full_bar[slot_i]);
-    bulk_load_1d(dst + C::XBYTES, wsrc, C::WBYTES, &full_bar[slot_i]);
-    if (tile + 1 == it.n_tiles) { cursor[0] = item + gridDim.x; cursor[1] = 0; }
-    else cursor[1] = tile + 1;
+    tma_load_2d(dst, &p.tmap[side], cursor[kCurGene0], row, &full_bar[slot_i]);
+    bulk_load_1d(dst + C::XBYTES, s.wtab + ((size_t)cursor[kCurGroup] * s.n_pad + (size_t)row) * C::RF, C::WBYTES,
+                 &full_bar[slot_i]);
+    const int left = cursor[kCurTilesLeft] - 1;
+    if (left == 0) {
+      cursor_set_item(cursor[kCurItem] + gridDim.x);
+    } else {
+      cursor[kCurTilesLeft] = left;
+      cursor[kCurRow] = row + kCellTile;
+    }
   };
   if (tid == 0) {
+    cursor_set_item(blockIdx.x);
     for (int s = 0; s < n_stages; ++s) issue_next(s);
     __threadfence_block();
   }
@@ -380,14 +398,12 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
           for (int x = 0; x < GX; ++x) cnt[x] += nonzero_flag(xt[cell * C::GT + lane * GX + x]);
         }
       }
-      __syncwarp();
+      __syncwarp();  // every lane's shared-memory reads of this stage have returned (values are in registers)
       if (lane == 0) {
-        __threadfence_block();
-        if (atomicAdd(&done[slot], 1) == kConsumerWarps - 1) {  // last warp out refills the stage
+        if (smem_atomic_inc(&done[slot]) == kConsumerWarps - 1) {  // last warp out refills the stage
           done[slot] = 0;
-          __threadfence_block();
+          __threadfence_block();   // counter reset ordered before the TMA completion the other warps wait for
           issue_next(slot);
-          __threadfence_block();
         }
       }
       if (++slot == n_stages) { slot = 0; phase ^= 1; }
@@ -461,7 +477,7 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
   G2G_CUDA_TRY(cudaGetDevice(&dev));
   G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const size_t fixed = (size_t)C::STAGING_BYTES + (size_t)C::NQ * C::GT * 8 + (size_t)p.n_bins * C::GT * 4 +
-                       8 * 8 + (8 + 2) * 4 + 128;
+                       8 * 8 + (8 + kCursorInts) * 4 + 128;
   // as many stages (<= 8, >= 2) as fit the shared memory of G2G_MOM_MIN_BLOCKS CTAs per SM
   int stages = 8;
   const size_t budget = (size_t)(C::kMinBlocks >= 2 ? 110 : 200) * 1024;
