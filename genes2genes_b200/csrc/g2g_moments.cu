@@ -52,9 +52,12 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-__device__ __forceinline__ int smem_atomic_inc(int* addr) {  // called by one lane: no warp-aggregation code
-  int old;
-  asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(addr)) : "memory");
+// Wrapping counter: returns the old value and stores old >= limit ? 0 : old + 1.  The arrival that sees
+// `limit` has also reset the counter, and ptxas emits a bare ATOMS.INC for it (an ATOMS.ADD gets wrapped
+// in warp-aggregation code even when a single lane runs it).
+__device__ __forceinline__ unsigned smem_atomic_inc_wrap(int* addr, unsigned limit) {
+  unsigned old;
+  asm volatile("atom.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(limit) : "memory");
   return old;
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -400,11 +403,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       }
       __syncwarp();  // every lane's shared-memory reads of this stage have returned (values are in registers)
       if (lane == 0) {
-        if (smem_atomic_inc(&done[slot]) == kConsumerWarps - 1) {  // last warp out refills the stage
-          done[slot] = 0;
-          __threadfence_block();   // counter reset ordered before the TMA completion the other warps wait for
-          issue_next(slot);
-        }
+        // last warp out refills the stage (its arrival also wraps the counter back to 0)
+        if (smem_atomic_inc_wrap(&done[slot], kConsumerWarps - 1) == kConsumerWarps - 1) issue_next(slot);
       }
       if (++slot == n_stages) { slot = 0; phase ^= 1; }
       if (++since_flush == kFlushStages && tile + 1 < it.n_tiles) { reduce_flush(false, it); since_flush = 0; }
