@@ -160,7 +160,8 @@ template <int TBE, int GX>
 __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_kernel(const __grid_constant__ MomParams p) {
   using C = Cfg<TBE, GX>;
   constexpr int NP = C::NP;
-  constexpr int kCellUnroll = (2 * TBE * GX <= 64) ? 2 : 1;
+  // small register tiles: all 8 cells of a stage straight-line; the 128-register ones keep 2 (no spills)
+  constexpr int kCellUnroll = (2 * TBE * GX <= 56) ? kCellsPerWarp : (2 * TBE * GX <= 64) ? 2 : 1;
   extern __shared__ __align__(128) unsigned char smem[];
   const int n_stages = p.n_stages;
   // layout: [stages][X tile | W slice] | staging | acc64 [NQ][GT] | cnt [n_bins][GT] | barriers, counters
