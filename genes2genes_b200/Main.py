@@ -149,6 +149,17 @@ def matched_time_points(s):
     return np.array(S_pts), np.array(T_pts)
 
 
+def _string_table(host):
+    """All 5-state strings of a batch decoded at once (cached in the result dict): (text, lengths,
+    stride).  Per-gene access is then a plain slice."""
+    tab = host.get("_strings")
+    if tab is None:
+        arr = host["align_str"]
+        tab = (arr.tobytes().decode("latin-1"), host["align_len"].tolist(), int(arr.shape[1]))  # bytes past a length are unspecified
+        host["_strings"] = tab
+    return tab
+
+
 class AligmentObj:
     """Alignment result of one gene (reference: Main.py:33-177; the class name keeps the
     reference's spelling).  A view over the aligner's batched arrays: constructing it costs O(1);
@@ -190,8 +201,13 @@ class AligmentObj:
         return self._store.host if self._host is None else self._host
 
     def _load_str(self):
-        h, idx = self._results(), self._gene_idx
-        self.alignment_str = h["align_str"][idx, :int(h["align_len"][idx])].tobytes().decode("ascii")
+        idx = self._gene_idx
+        if self._host is not None:   # single-gene re-alignment (align_single_pair)
+            h = self._host
+            self.alignment_str = h["align_str"][idx, :int(h["align_len"][idx])].tobytes().decode("ascii")
+            return
+        text, lens, stride = _string_table(self._store.host)
+        self.alignment_str = text[idx * stride:idx * stride + lens[idx]]
 
     def _load_series(self):
         self.S, self.T = self._store.pairs[self.gene]
@@ -487,7 +503,7 @@ class RefQueryAligner:
                 # one side fell over the density threshold: densify the sparse one too
                 self._both_sparse = False
                 if isinstance(Xr, _engine.CscMatrix):
-                    Xr = self._pack(adata_ref, self.TrajInt_R.order, raw_ref)
+                    Xr = self._pack(adata_ref, self.TrajInt_R.order)
                 else:
                     Xq = self._pack(adata_query, self.TrajInt_Q.order)
             self._engine = _engine.AlignmentEngine(

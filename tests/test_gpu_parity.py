@@ -514,6 +514,36 @@ def test_sparse_csc_path_equals_dense_path(T):
             assert abs(a_obj.fwd_DP.opt_cost - dense["opt_cost"][g]) <= 5e-5 * abs(dense["opt_cost"][g])
 
 
+def test_api_sparse_inputs_of_mixed_density_are_both_densified():
+    """Two scipy-sparse inputs on different sides of ``sparse_density_threshold``: the sparse K1s
+    needs both sides in CSC form, so the aligner densifies both on the device and the results are
+    bitwise those of dense inputs."""
+    sp = pytest.importorskip("scipy.sparse")
+    from genes2genes_b200 import Main
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    G, nr, nq, T = 64, 600, 500, 14
+    Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=0.95, seed=11)
+    Xq = Xq.copy()
+    # half of the query columns have no zeros (varying offsets: a constant column has no variance)
+    Xq[:, ::2] += np.random.default_rng(3).uniform(0.01, 0.02, Xq[:, ::2].shape).astype(np.float32)
+    dr, dq = np.count_nonzero(Xr) / Xr.size, np.count_nonzero(Xq) / Xq.size
+    assert dr < dq
+    base = Main.RefQueryAligner(AnnDataLite(Xr, tr, genes), AnnDataLite(Xq, tq, genes), genes, T, verbose=False)
+    base.align_all_pairs()
+    saved = Main.RefQueryAligner.sparse_density_threshold
+    Main.RefQueryAligner.sparse_density_threshold = 0.5 * (dr + dq)
+    try:
+        al = Main.RefQueryAligner(AnnDataLite(sp.csr_matrix(Xr), tr, genes), AnnDataLite(sp.csr_matrix(Xq), tq, genes),
+                                  genes, T, verbose=False)
+    finally:
+        Main.RefQueryAligner.sparse_density_threshold = saved
+    assert not al._engine.sparse
+    al.align_all_pairs()
+    for a_obj, b_obj in zip(al.results, base.results):
+        assert a_obj.alignment_str == b_obj.alignment_str
+        assert a_obj.fwd_DP.opt_cost == b_obj.fwd_DP.opt_cost
+
+
 def test_string_distance_matrices(golden_dir):
     """f4: Levenshtein (Myers bit-vector kernel) and Hamming distance matrices are exact: equal to the
     oracle's dynamic programme / scipy-style Hamming on real and random alignment strings, including
