@@ -604,9 +604,10 @@ class RefQueryAligner:
         with torch.cuda.device(self.device):
             eng.set_state_params(self.state_params)
             if self._interp is None:
-                eng.run_interpolation()
+                eng.run_interpolation(with_dp=True)   # interpolation + fix-up + DP, fused launch
                 self._interp = True
-            eng.run_dp()
+            else:
+                eng.run_dp()                          # new state_params: only the DP is repeated
             host = eng.results_to_host() if self._dist is None else self._gather_results()
         self._store = _ResultStore(host, self.gene_list, self.n_artificial_time_points, eng.eps,
                                    self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,

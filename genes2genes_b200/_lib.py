@@ -50,6 +50,9 @@ SIGNATURES = {
                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_cost_dp": (c_i32, [c_vp, c_i64, c_i32, ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, c_i32,
                             c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "g2g_fixup_cost_dp": (c_i32, [ctypes.POINTER(Side), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32,
+                                  ctypes.POINTER(c_f64), ctypes.POINTER(c_f64), c_f64, c_i32,
+                                  c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "g2g_state_histogram": (c_i32, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "g2g_match_counts": (c_i32, [c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_vp]),
     "g2g_strdist_workspace_bytes": (c_sz, [c_i64]),

@@ -323,7 +323,9 @@ class AlignmentEngine:
         self.trans = transition_costs(self.free_params)
 
     # -- stages -----------------------------------------------------------------------------
-    def run_interpolation(self):
+    def run_interpolation(self, with_dp=False):
+        """K0 / pilot / K1 and the per-gene fix-up.  ``with_dp=True`` finishes with the fused fix-up +
+        cost + DP launch (``g2g_fixup_cost_dp``) instead of ``g2g_fixup_trends``: the whole hot path."""
         lib, T, G = self.lib, self.n_bins, self.n_genes
         cur = torch.cuda.current_stream()
         # four independent small kernels: the weight tables of the two datasets go to two forked streams,
@@ -347,6 +349,16 @@ class AlignmentEngine:
             _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
         else:
             _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+        if with_dp:
+            trans_c = (c_f64 * 25)(*np.asarray(self.trans, dtype=np.float64).reshape(-1).tolist())
+            start_c = (c_f64 * 3)(*np.asarray(self.start, dtype=np.float64).tolist())
+            _lib.check(lib.g2g_fixup_cost_dp(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w),
+                                             _ptr(self.points), _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T,
+                                             trans_c, start_c, float(self.c_model), N_SAMPLES, _ptr(self.musigma),
+                                             _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags),
+                                             _ptr(self.align_str), _ptr(self.align_len), _ptr(self.opt_cost),
+                                             _ptr(self.l_states), st), "g2g_fixup_cost_dp")
+            return 4 if self.sparse else 6  # 2 x (weights[, pilot]) + moments + fused fix-up / DP
         _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
                                         _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
                                         _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), _ptr(self.fix_ws),
@@ -378,10 +390,15 @@ class AlignmentEngine:
                        "g2g_moments")
         end_event.record()
 
-    def run(self):
-        n = self.run_interpolation()
-        self.run_dp()
-        self.launches_per_run = n + 1
+    def run(self, fused=True):
+        """The whole hot path on the current stream.  ``fused=False`` runs the fix-up and the DP as the
+        two separate entry points (same results bit for bit; one more launch and a workspace pass)."""
+        if fused:
+            self.launches_per_run = self.run_interpolation(with_dp=True)
+        else:
+            n = self.run_interpolation()
+            self.run_dp()
+            self.launches_per_run = n + 1
         return self
 
     RESULT_KEYS = ("opt_cost", "trends", "musigma", "align_len", "flags", "nnz", "align_str", "l_states")

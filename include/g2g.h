@@ -209,6 +209,19 @@ int g2g_cost_dp(const double* trends, int64_t n_genes, int32_t n_bins, const dou
                 double* cost_out, double* mats_out, int8_t* bp_out, double* l_out, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * K3+K4  g2g_fixup_cost_dp -- g2g_fixup_trends followed by g2g_cost_dp (compact outputs only) as ONE
+ * kernel launch: the production path of RefQueryAligner.align_all_pairs (Main.py:434-457 calling
+ * run_interpolation and align_single_pair per gene).  Same arguments and bit-identical outputs as the
+ * two calls; no workspace (the split totals of a block's genes stay in shared memory).
+ */
+int g2g_fixup_cost_dp(const g2g_side_t* sides, const double* sum_w_ref, const double* sum_w_query,
+                      const double* points, const double* eps_mean, const double* eps_std,
+                      int64_t n_genes, int64_t g_stride, int32_t n_bins, const double* trans,
+                      const double* start, double c_model, int32_t n_samples, double* musigma,
+                      double* trends, int32_t* nnz, int32_t* flags, uint8_t* align_str,
+                      int32_t* align_len, double* opt_cost, uint8_t* l_states, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Aggregate (cell-level) alignment over a gene set -- SURVEY.md 8(f) row f2.
  * g2g_state_histogram: counts[k][cell] = number of selected genes whose landscape state at DP cell
  *   `cell` is k (M,W,V,D,I); replaces the counting loop of ClusterUtils.get_cluster_average_alignments

@@ -238,6 +238,17 @@ def test_pipeline_vs_batched_oracle(shape):
         assert o.backtrack(mats[g], bp[g])[0] == got[g]
 
 
+def test_fused_fixup_dp_launch_equals_separate_calls():
+    """``g2g_fixup_cost_dp`` (one launch) against ``g2g_fixup_trends`` + ``g2g_cost_dp``: every output
+    bitwise equal, for the 4 / 2 / 1 genes-per-warp variants and a multi-column-per-lane one."""
+    for G, nr, nq, T, seed in ((203, 900, 700, 14, 3), (61, 500, 400, 7, 4), (50, 400, 300, 29, 5), (21, 300, 300, 50, 6)):
+        Xr, tr, Xq, tq, _ = synthetic.make_pair(G, nr, nq, dropout=0.8, seed=seed)
+        a = _engine_from_arrays(Xr, tr, Xq, tq, T).run(fused=True).results_to_host()
+        b = _engine_from_arrays(Xr, tr, Xq, tq, T).run(fused=False).results_to_host()
+        for k in a:
+            assert np.array_equal(a[k], b[k]), (k, T)
+
+
 def test_moments_run_to_run_and_shard_invariance():
     """K1 sums in an order fixed by (n_cells, n_bins): two runs are bitwise equal, and a gene's
     result does not depend on which other genes are in the batch (multi-GPU sharding, 8(e))."""
