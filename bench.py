@@ -141,7 +141,7 @@ def run_reference(args):
             "config": config_dict(args.workload, args.dropout, args.gpus),
             "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -445,7 +445,7 @@ def run_b200(args):
                                     "sample": "%d genes of the workload at full cell counts, oracle port "
                                               "(oracle/g2g_oracle.py align_gene_faithful), %.1f s"
                                               % (min(args.cpu_genes, G), time.perf_counter() - t0)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         del graph
         torch.cuda.synchronize()
@@ -453,8 +453,27 @@ def run_b200(args):
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The contract's ONE JSON line goes to the process's original stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
+    global _RESULT_FD
     args = parse_args()
+    # anything a library prints on stdout (NCCL's version banner, warnings) must not mix with the result
+    # line: file descriptor 1 is pointed at stderr for the run and the line is written to the saved one
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
