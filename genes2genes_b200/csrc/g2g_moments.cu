@@ -139,6 +139,9 @@ __device__ __forceinline__ void ffma2_bcast(unsigned long long& acc, unsigned lo
 }
 // 1 where x != 0 (NaN counts as non-zero, like np.count_nonzero), else 0, in one FMNMX: the bit
 // pattern of min(|x|, smallest denormal) is the integer 0 or 1 (f32 denormals are not flushed here)
+#ifdef __CUDA_FTZ
+#error "g2g_moments.cu must be compiled without -ftz=true / --use_fast_math: nonzero_flag() relies on f32 denormals"
+#endif
 __device__ __forceinline__ int nonzero_flag(float x) { return __float_as_int(fminf(fabsf(x), __int_as_float(1))); }
 __device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
   unsigned long long d;

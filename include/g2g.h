@@ -51,7 +51,9 @@ int g2g_check_device(void);
 
 /* How the interpolation kernels tile `n_bins`: bins are split into `n_groups` groups of
  * `bins_per_group` (last group zero-padded); one row of the weight table holds, per group,
- * `row_floats` floats = [w_0 .. w_{bins_per_group-1}, valid, window_id(int bits), 0-pad]. */
+ * `row_floats` floats = [w_0 .. w_{bins_per_group-1}, (0 when that count is odd), valid, window_id(int bits),
+ * 0-pad].  window_id = k for p_k <= tau < p_{k+1}, n_bins-1 outside every window, -1 for padding rows, plus
+ * 0x10000 when the aligned group of 8 rows the cell belongs to spans more than one window. */
 typedef struct {
   int32_t n_groups;
   int32_t bins_per_group;
