@@ -598,7 +598,11 @@ class RefQueryAligner:
             self._run_batch()
         return self._store.pairs
 
-    def _run_batch(self):
+    def _run_batch(self, on_enqueued=None, store=None):
+        """Enqueue the batch, copy the compact results back and build (or fill ``store``, a result store
+        made ahead of time) the result store.  ``on_enqueued`` (single-process runs) is called after
+        everything is queued and before the host waits for the device: host-side work done there
+        overlaps the GPU."""
         import torch
         eng = self._engine
         with torch.cuda.device(self.device):
@@ -608,10 +612,18 @@ class RefQueryAligner:
                 self._interp = True
             else:
                 eng.run_dp()                          # new state_params: only the DP is repeated
-            host = eng.results_to_host() if self._dist is None else self._gather_results()
-        self._store = _ResultStore(host, self.gene_list, self.n_artificial_time_points, eng.eps,
-                                   self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
-                                   self.state_params, self.device)
+            if self._dist is None:
+                eng.begin_results_to_host()
+                if on_enqueued is not None:
+                    on_enqueued()
+                host = eng.finish_results_to_host()
+            else:
+                host = self._gather_results()
+        if store is None:
+            store = self._new_store(host)
+        else:
+            store.host = host
+        self._store = store
         bad = np.nonzero(host["flags"] & _FLAG_BAD_SIGMA)[0]
         if len(bad):
             g = self.gene_list[int(bad[0])]
@@ -619,6 +631,11 @@ class RefQueryAligner:
                              "(GreaterThan(lower_bound=0.0)); gene %r has a zero or invalid interpolated "
                              "standard deviation (%d gene(s) affected)" % (g, len(bad)))
         return host
+
+    def _new_store(self, host):
+        return _ResultStore(host, self.gene_list, self.n_artificial_time_points, self._engine.eps,
+                            self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
+                            self.state_params, self.device)
 
     def _gather_results(self):
         """The one collective of the path: every rank's per-gene records go to rank 0 (NCCL gather)."""
@@ -673,8 +690,20 @@ class RefQueryAligner:
         ``n_processes`` are accepted for signature compatibility; the batch already runs all genes
         concurrently on the GPU."""
         self._say("Running gene-level alignment: \U0001F9EC")
-        self._run_batch()
-        self.results = [self._make_result(k) for k in range(len(self.gene_list))]
+        if self._dist is not None:
+            self._run_batch()                                   # rank 0's gene_list grows to all genes here
+            store = self._store
+            self.results = [AligmentObj(store, k, g) for k, g in enumerate(self.gene_list)]
+        else:
+            # the result objects are O(1) views: build them while the GPU is still working
+            store = self._new_store(None)
+            built = []
+            self._run_batch(on_enqueued=lambda: built.extend(
+                AligmentObj(store, k, g) for k, g in enumerate(self.gene_list)), store=store)
+            self.results = built
+        text, lens, stride = _string_table(store.host)
+        for k, a in enumerate(self.results):                    # strings are cheap to cut here, dear to cut lazily
+            a.alignment_str = text[k * stride:k * stride + lens[k]]
         self.results_map = {a.gene: a for a in self.results}
         self._say("Alignment completed! ✅")
 

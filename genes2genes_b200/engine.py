@@ -407,17 +407,28 @@ class AlignmentEngine:
         """All result arrays in ONE device->host copy: they are packed into a byte buffer on the
         device (8-, 4-, then 1-byte element types so every view stays aligned) and land in a
         pinned host buffer."""
+        self.begin_results_to_host()
+        return self.finish_results_to_host()
+
+    def begin_results_to_host(self):
+        """Enqueue the packed device->host copy on the current stream and return at once."""
         parts = [getattr(self, k) for k in self.RESULT_KEYS]
         packed = torch.cat([t.view(torch.uint8).reshape(-1) for t in parts])
         if self._host_buf is None or self._host_buf.numel() != packed.numel():
             self._host_buf = _pinned_buffer(packed.numel())
         self._host_buf.copy_(packed, non_blocking=True)
+        self._pending_parts = parts
+
+    def finish_results_to_host(self):
+        """Wait for the copy started by ``begin_results_to_host``; returns name -> numpy array (views of
+        one private host copy of the staging buffer, which is reused by later calls)."""
         torch.cuda.current_stream().synchronize()
-        raw = self._host_buf.numpy()
+        parts, self._pending_parts = self._pending_parts, None
+        raw = self._host_buf.numpy().copy()
         host, off = {}, 0
         for k, t in zip(self.RESULT_KEYS, parts):
             n = t.numel() * t.element_size()
-            host[k] = raw[off:off + n].view(_NP_DTYPES[t.dtype]).reshape(tuple(t.shape)).copy()
+            host[k] = raw[off:off + n].view(_NP_DTYPES[t.dtype]).reshape(tuple(t.shape))
             off += n
         return host
 
