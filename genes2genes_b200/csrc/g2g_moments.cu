@@ -186,7 +186,6 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int k = tid; k < C::NQ * C::GT; k += kThreads) acc64[k] = 0.0;
   for (int k = tid; k < p.n_bins * C::GT; k += kThreads) cnt_s[k] = 0;
   __syncthreads();
 
@@ -246,6 +245,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
   // stores its partial sums to the staging area; thread k then adds the eight values of slot k in
   // warp order to the CTA's f64 accumulator -- a fixed summation order.  `final` also adds the f64
   // accumulator, writes the item's result to global memory and clears it.
+  bool acc64_used = false;   // a non-final flush of the current item has left sums in acc64
   auto reduce_flush = [&](bool final, const Item& it) {
     const MomSide& s = p.side[it.side];
     const int T = p.n_bins, TB = p.bins_per_group;
@@ -278,7 +278,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
 #pragma unroll
         for (int w = 0; w < kConsumerWarps; ++w) sum += (double)staging[(size_t)w * C::kRows * C::GT + k];
         const int slot64 = r0 * C::GT + k;
-        sum += acc64[slot64];
+        if (acc64_used) sum += acc64[slot64];
         if (final) {
           const int q = slot64 / C::GT, gl = slot64 % C::GT;
           const long long g = g0 + gl;
@@ -287,13 +287,13 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
           else if (q < 2 * TBE) { int t = it.bg * TB + (q - TBE); if (q - TBE < TB && t < T) row = T + t; }
           else if (it.bg == 0) row = 2 * T;
           if (row >= 0 && g < p.n_genes) pf[(size_t)row * p.g_stride + g] = sum;
-          acc64[slot64] = 0.0;
         } else {
           acc64[slot64] = sum;
         }
       }
       __syncthreads();
     }
+    acc64_used = !final;
     accC2 = 0ull;
 #pragma unroll
     for (int x = 0; x < GX; ++x) {

@@ -106,7 +106,15 @@ __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams 
     for (int k = threadIdx.x; k < T * 16; k += kWThreads) {
       const int t = k >> 4, q = k & 15;
       double r = 0.0;
-      for (unsigned int b = q; b < gridDim.x; b += 16) r += p.partial[(size_t)b * T + t];
+      unsigned int b = q;
+      for (; b + 7 * 16 < gridDim.x; b += 8 * 16) {   // eight loads in flight, additions in block order
+        double v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = p.partial[(size_t)(b + 16 * j) * T + t];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r += v[j];
+      }
+      for (; b < gridDim.x; b += 16) r += p.partial[(size_t)b * T + t];
       s_w[t][q] = r;
     }
     __syncthreads();
