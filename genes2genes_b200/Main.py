@@ -149,14 +149,15 @@ def matched_time_points(s):
     return np.array(S_pts), np.array(T_pts)
 
 
-def _string_table(host):
-    """All 5-state strings of a batch decoded at once (cached in the result dict): (text, lengths,
+def _string_table(store):
+    """All 5-state strings of a batch decoded at once (cached on the result store): (text, lengths,
     stride).  Per-gene access is then a plain slice."""
-    tab = host.get("_strings")
+    tab = store.strings
     if tab is None:
-        arr = host["align_str"]
-        tab = (arr.tobytes().decode("latin-1"), host["align_len"].tolist(), int(arr.shape[1]))  # bytes past a length are unspecified
-        host["_strings"] = tab
+        arr = store.host["align_str"]
+        # bytes past a string's length are zero; latin-1 maps every byte to one character
+        tab = (arr.tobytes().decode("latin-1"), store.host["align_len"].tolist(), int(arr.shape[1]))
+        store.strings = tab
     return tab
 
 
@@ -206,7 +207,7 @@ class AligmentObj:
             h = self._host
             self.alignment_str = h["align_str"][idx, :int(h["align_len"][idx])].tobytes().decode("ascii")
             return
-        text, lens, stride = _string_table(self._store.host)
+        text, lens, stride = _string_table(self._store)
         self.alignment_str = text[idx * stride:idx * stride + lens[idx]]
 
     def _load_series(self):
@@ -375,6 +376,7 @@ class _ResultStore:
         self.state_params = tuple(state_params)
         self.device = device
         self.de = None
+        self.strings = None
         self.pairs = _LazyPairs(self)
 
     def series_pair(self, idx):
@@ -701,7 +703,7 @@ class RefQueryAligner:
             self._run_batch(on_enqueued=lambda: built.extend(
                 AligmentObj(store, k, g) for k, g in enumerate(self.gene_list)), store=store)
             self.results = built
-        text, lens, stride = _string_table(store.host)
+        text, lens, stride = _string_table(store)
         for k, a in enumerate(self.results):                    # strings are cheap to cut here, dear to cut lazily
             a.alignment_str = text[k * stride:k * stride + lens[k]]
         self.results_map = {a.gene: a for a in self.results}

@@ -58,13 +58,16 @@ class ResultGather:
         self.dst, self.group = dst, group
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
-        probe = pack_records({k: getattr(source, k) for k in RECORD_KEYS})
-        self.send = torch.empty_like(probe)
+        # an engine keeps its records packed in this very layout: send that buffer as it is
+        self.packed = getattr(source, "packed", None)
+        probe = self.packed if self.packed is not None else pack_records({k: getattr(source, k) for k in RECORD_KEYS})
+        self.send = probe if self.packed is not None else torch.empty_like(probe)
         self.recv = [torch.empty_like(probe) for _ in range(self.world)] if self.rank == dst else None
 
     def run(self):
-        torch.cat([getattr(self.source, k).contiguous().view(torch.uint8).reshape(-1) for k in RECORD_KEYS],
-                  out=self.send)
+        if self.packed is None:
+            torch.cat([getattr(self.source, k).contiguous().view(torch.uint8).reshape(-1) for k in RECORD_KEYS],
+                      out=self.send)
         dist.gather(self.send, self.recv, dst=self.dst, group=self.group)
         return self.recv
 

@@ -297,14 +297,19 @@ class AlignmentEngine:
         self.set_state_params(free_params)
         self.start = start_costs()
         self.c_model = model_constant()
-        self.musigma = torch.empty((G, 4, T), **f64)
-        self.trends = torch.empty((G, 4, T), **f64)
-        self.nnz = torch.empty((G, 2), dtype=torch.int32, device=dev)
-        self.flags = torch.empty(G, dtype=torch.int32, device=dev)
-        self.align_str = torch.empty((G, 2 * T), dtype=torch.uint8, device=dev)
-        self.align_len = torch.empty(G, dtype=torch.int32, device=dev)
-        self.opt_cost = torch.empty(G, **f64)
-        self.l_states = torch.empty((G, (T + 1) * (T + 1)), dtype=torch.uint8, device=dev)
+        # every per-gene result lives in ONE packed byte buffer (8-, 4-, then 1-byte element types, so
+        # each view is aligned): the device->host copy and the multi-GPU gather move it as it is
+        shapes = {"opt_cost": ((G,), torch.float64), "trends": ((G, 4, T), torch.float64),
+                  "musigma": ((G, 4, T), torch.float64), "align_len": ((G,), torch.int32),
+                  "flags": ((G,), torch.int32), "nnz": ((G, 2), torch.int32),
+                  "align_str": ((G, 2 * T), torch.uint8), "l_states": ((G, (T + 1) * (T + 1)), torch.uint8)}
+        sizes = [int(np.prod(shapes[k][0])) * torch.empty((), dtype=shapes[k][1]).element_size()
+                 for k in self.RESULT_KEYS]
+        self.packed = torch.empty(max(sum(sizes), 8), dtype=torch.uint8, device=dev)
+        off = 0
+        for k, n in zip(self.RESULT_KEYS, sizes):
+            setattr(self, k, self.packed[off:off + n].view(shapes[k][1]).reshape(shapes[k][0]))
+            off += n
         self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
         self._sparse_sides = (SparseSide * 2)(self.ref.c_sparse_side(), self.query.c_sparse_side()) \
             if self.sparse else None
@@ -412,12 +417,10 @@ class AlignmentEngine:
 
     def begin_results_to_host(self):
         """Enqueue the packed device->host copy on the current stream and return at once."""
-        parts = [getattr(self, k) for k in self.RESULT_KEYS]
-        packed = torch.cat([t.view(torch.uint8).reshape(-1) for t in parts])
-        if self._host_buf is None or self._host_buf.numel() != packed.numel():
-            self._host_buf = _pinned_buffer(packed.numel())
-        self._host_buf.copy_(packed, non_blocking=True)
-        self._pending_parts = parts
+        if self._host_buf is None or self._host_buf.numel() != self.packed.numel():
+            self._host_buf = _pinned_buffer(self.packed.numel())
+        self._host_buf.copy_(self.packed, non_blocking=True)
+        self._pending_parts = [getattr(self, k) for k in self.RESULT_KEYS]
 
     def finish_results_to_host(self):
         """Wait for the copy started by ``begin_results_to_host``; returns name -> numpy array (views of
