@@ -306,7 +306,7 @@ def run_b200(args):
     torch.cuda.synchronize()
     graph = None
     if not args.no_graph:
-        # the 8 kernel launches of a step replay as one CUDA graph; the NCCL gather (N > 1) stays an
+        # the 6 kernel launches of a step replay as one CUDA graph; the NCCL gather (N > 1) stays an
         # eager call after the replay (a captured collective hung process-group teardown on this stack)
         try:
             g = torch.cuda.CUDAGraph()

@@ -4,16 +4,20 @@
 // and the non-zero counts per pseudotime window.  Replaces the per-gene pandas/numpy loop of
 // TimeSeriesPreprocessor.compute_stat (TSP.py:161-174) and the counts of Main.py:298-301,344-363.
 //
-// Structure (B200): persistent CTAs walk a static list of work items (gene tile x cell range).
-// [64 cells x GT genes] tiles of X are streamed with TMA (cp.async.bulk.tensor.2d) and the matching
-// 64 rows of the weight table with a 1-D bulk copy into a ring of shared-memory stages guarded by
-// mbarriers; the warp that finishes a stage last re-arms it with the next tile, so there is no
-// producer warp and no blocking hand-off.  Eight warps each take 8 cells of a stage; every thread owns GX
-// genes x TB bins x {A,B} float accumulators in registers (an FFMA register tile: the weights are
-// warp-broadcast LDS.128, X is a conflict-free LDS; two bins are packed per FFMA2).  Every
-// kFlushStages stages, and at the end of an item, the eight warps' f32 partials are summed in f64 in
-// a fixed order through a shared staging area, so results do not depend on scheduling; the item's
-// f64 sums go to its own slot of `part_f64`.
+// Structure (B200): persistent CTAs (two per SM while the register tile allows) walk a static list of
+// work items (gene tile x cell range).  [64 cells x GT genes] tiles of X are streamed with TMA
+// (cp.async.bulk.tensor.2d) and the matching 64 rows of the weight table with a 1-D bulk copy into a
+// ring of shared-memory stages guarded by mbarriers; the warp that finishes a stage last (a wrapping
+// shared-memory counter) re-arms it from a cursor kept decoded in shared memory, so there is no producer
+// warp, no blocking hand-off and no per-tile index arithmetic.  Eight warps each take 8 cells of a stage;
+// every thread owns GX genes x TB bins x {A,B} float accumulators in registers (an FFMA2 register tile:
+// the weights are warp-broadcast LDS.128, X is a conflict-free LDS, two bins per packed FFMA2, and with
+// GX = 2 the d / d^2 / C arithmetic of the two genes is packed too).  The kernel is bound by FP32
+// instruction issue, so the loop is kept to FFMA2 plus the fewest other instructions: non-zero counting
+// is one FMNMX per value, window bookkeeping happens per 8-cell group (K0 flags the groups that straddle
+// a window boundary).  Every kFlushStages stages, and at the end of an item, the eight warps' f32
+// partials are summed in f64 in a fixed order through a shared staging area, so results do not depend
+// on scheduling; the item's f64 sums go to its own slot of `part_f64`.
 #include "g2g_common.cuh"
 #include <cuda.h>
 #include <stdlib.h>

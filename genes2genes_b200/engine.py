@@ -269,8 +269,8 @@ def pack_csc(csr, row_order, gene_idx, n_all_genes, device):
 class AlignmentEngine:
     """Runs the whole hot path for one (reference, query) pair of packed device matrices.
 
-    ``run()`` enqueues K0 (weights) + K1a (pilot) + K1 (moments) + K3 (fix-up / trends) + K4
-    (cost + DP + traceback) on the current stream and returns the device result tensors.
+    ``run()`` enqueues K0 (weights) + K1a (pilot) + K1 (moments) and the fused K3 + K4 launch (fix-up /
+    trends, cost + DP + traceback) and returns itself; the results are views of ``self.packed``.
     """
 
     def __init__(self, X_ref, tau_ref, X_query, tau_query, n_genes, n_bins, denom_ref, denom_query,
