@@ -6,15 +6,15 @@
 namespace {
 
 // Stage 1: sum the per-split partials of K1, one thread per (side, row, gene); coalesced over genes.
-__global__ void __launch_bounds__(256) reduce_partials_kernel(const ReduceParams p) {
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const __grid_constant__ ReduceParams p) {
   const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= p.n_genes) return;
   const int T = p.n_bins;
   const int rows_per_side = 3 * T + 1;
   const int side = blockIdx.y / rows_per_side;
   const int row = blockIdx.y % rows_per_side;
-  if (row < 2 * T + 1) p.red_f64[side][(size_t)row * p.g_stride + g] = reduce_f64_row(p, side, row, g);
-  else p.red_i32[side][(size_t)(row - (2 * T + 1)) * p.g_stride + g] = reduce_i32_row(p, side, row - (2 * T + 1), g);
+  if (row < 2 * T + 1) p.red_f64[side][(size_t)row * p.g_stride + g] = reduce_f64_row<8>(p, side, row, g);
+  else p.red_i32[side][(size_t)(row - (2 * T + 1)) * p.g_stride + g] = reduce_i32_row<8>(p, side, row - (2 * T + 1), g);
 }
 
 constexpr int kFixWarps = 4;

@@ -43,10 +43,9 @@ struct ReduceParams {
 };
 
 // Sum of one (side, row, gene) over the splits, in split order (fixed => deterministic); the loads
-// are issued twelve at a time (the partial sums sit in L2, latency bound), the additions stay sequential.
-template <typename V>
+// are issued kBatch at a time (the partial sums sit in L2, latency bound), the additions stay sequential.
+template <int kBatch, typename V>
 __device__ __forceinline__ V reduce_splits(const V* src, size_t plane, long long ns) {
-  constexpr int kBatch = 12;
   V r = 0;
   long long k = 0;
   for (; k + kBatch <= ns; k += kBatch) {
@@ -61,17 +60,18 @@ __device__ __forceinline__ V reduce_splits(const V* src, size_t plane, long long
 #pragma unroll
     for (int j = 0; j < kBatch; ++j) v[j] = (k + j < ns) ? src[(size_t)(k + j) * plane] : V(0);
 #pragma unroll
-    for (int j = 0; j < kBatch; ++j)
-      if (k + j < ns) r += v[j];
+    for (int j = 0; j < kBatch; ++j) r += v[j];   // + 0 past the end: r is never -0.0, so bits are unchanged
   }
   return r;
 }
+template <int kBatch>
 __device__ __forceinline__ double reduce_f64_row(const ReduceParams& p, int side, int row, long long g) {
-  return reduce_splits(p.part_f64[side] + (size_t)row * p.g_stride + g, (size_t)(2 * p.n_bins + 1) * p.g_stride,
+  return reduce_splits<kBatch>(p.part_f64[side] + (size_t)row * p.g_stride + g, (size_t)(2 * p.n_bins + 1) * p.g_stride,
                        p.n_split[side]);
 }
+template <int kBatch>
 __device__ __forceinline__ int reduce_i32_row(const ReduceParams& p, int side, int q, long long g) {
-  return reduce_splits(p.part_i32[side] + (size_t)q * p.g_stride + g, (size_t)p.n_bins * p.g_stride, p.n_split[side]);
+  return reduce_splits<kBatch>(p.part_i32[side] + (size_t)q * p.g_stride + g, (size_t)p.n_bins * p.g_stride, p.n_split[side]);
 }
 
 // Main.py:293-304 + 261-291 on the window flags (bit k = window [p_k, p_{k+1}) has <= 3 non-zero

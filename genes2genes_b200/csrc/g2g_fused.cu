@@ -27,6 +27,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * (32 / LW) * 32) fixup_dp_kern
   constexpr int GPW = 32 / LW;
   constexpr int GPC = kWarpsPerBlock * GPW;   // genes per block = warps per block
   constexpr int kThreads = GPC * 32;
+  constexpr int kLoads = B == 1 ? 24 : 12;   // loads in flight per thread in the split reduction (register room)
   const int T = q.fix.n_bins;
   const int rows_f = 2 * T + 1;
   double* tot_f = reinterpret_cast<double*>(smem_raw);                  // [2][2T+1][GPC]
@@ -39,8 +40,8 @@ __global__ void __launch_bounds__(kWarpsPerBlock * (32 / LW) * 32) fixup_dp_kern
     const int side = r / rows, row = r - side * rows;
     const long long g = g0 + gl;
     if (g < q.fix.n_genes) {
-      if (row < rows_f) tot_f[((size_t)side * rows_f + row) * GPC + gl] = reduce_f64_row(q.red, side, row, g);
-      else tot_i[((size_t)side * T + (row - rows_f)) * GPC + gl] = reduce_i32_row(q.red, side, row - rows_f, g);
+      if (row < rows_f) tot_f[((size_t)side * rows_f + row) * GPC + gl] = reduce_f64_row<kLoads>(q.red, side, row, g);
+      else tot_i[((size_t)side * T + (row - rows_f)) * GPC + gl] = reduce_i32_row<kLoads>(q.red, side, row - rows_f, g);
     }
   }
   __syncthreads();
