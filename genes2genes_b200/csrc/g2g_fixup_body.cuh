@@ -74,29 +74,53 @@ __device__ __forceinline__ int reduce_i32_row(const ReduceParams& p, int side, i
   return reduce_splits<kBatch>(p.part_i32[side] + (size_t)q * p.g_stride + g, (size_t)p.n_bins * p.g_stride, p.n_split[side]);
 }
 
+// 128-bit helpers for the window masks (bit k = window [p_k, p_{k+1}))
+__device__ __forceinline__ Mask128 mask_below(int k) {   // bits 0 .. k-1
+  Mask128 m;
+  m.lo = k >= 64 ? ~0ull : ((1ull << k) - 1ull);
+  m.hi = k <= 64 ? 0ull : (k >= 128 ? ~0ull : ((1ull << (k - 64)) - 1ull));
+  return m;
+}
+__device__ __forceinline__ int mask_msb(const Mask128& m) {   // highest set bit; m must not be empty
+  return m.hi ? 127 - __clzll((long long)m.hi) : 63 - __clzll((long long)m.lo);
+}
+__device__ __forceinline__ int mask_lsb(const Mask128& m) {   // lowest set bit; m must not be empty
+  return m.lo ? __ffsll((long long)m.lo) - 1 : 63 + __ffsll((long long)m.hi);
+}
+
 // Main.py:293-304 + 261-291 on the window flags (bit k = window [p_k, p_{k+1}) has <= 3 non-zero
 // cells); returns the mask of interpolation points whose value appears in the significant-region
-// list (np.in1d(points, regions), Main.py:356...).
-__device__ Mask128 region_mask(const Mask128& flagged, int T, const double* pts) {
+// list (np.in1d(points, regions), Main.py:356...).  The reference walks the flagged windows in
+// order, groups adjacent ones into runs [a, b], keeps a run when p_{b+1} - p_a > 0.2 -- except that the
+// run ending at the last flagged window is kept only when it has >= 2 windows (Main.py:283) -- and
+// lists the points a .. b+1 of every kept run.  Here every lane takes the windows t = 32 c + lane, finds
+// the bounds of the run its window belongs to with bit scans, decides `keep`, and the warp assembles the
+// point mask from ballots: point t is listed iff window t or window t-1 lies in a kept run.  Must be
+// called by all 32 lanes; every lane gets the whole mask.
+__device__ __forceinline__ Mask128 region_mask(const Mask128& flagged, int T, const double* pts, int lane) {
   Mask128 m = {0ull, 0ull};
-  int last_flag = -1;
-  for (int k = 0; k + 1 < T; ++k)
-    if (flagged.get(k)) last_flag = k;
-  if (last_flag < 0) return m;
-  int run_start = -1;
-  for (int k = 0; k + 1 < T; ++k) {
-    const bool f = flagged.get(k);
-    if (f && run_start < 0) run_start = k;
-    const bool next_f = (k + 2 < T) && flagged.get(k + 1);
-    if (f && !next_f) {  // run [run_start, k] ends here
-      const bool is_last_run = (k == last_flag);
-      const bool long_enough = (pts[k + 1] - pts[run_start]) > 0.2;
-      // a run that ends at the last flagged window is kept only when it has >= 2 windows (Main.py:283)
-      const bool keep = long_enough && (!is_last_run || k > run_start);
-      if (keep)
-        for (int b = run_start; b <= k + 1; ++b) m.set(b);
-      run_start = -1;
+  if (!flagged.any()) return m;
+  const int last_flag = mask_msb(flagged);
+  const Mask128 clear = {~flagged.lo, ~flagged.hi};   // bits >= T-1 are never flagged, so a run always ends
+  unsigned carry = 0u;
+  const int n_chunks = (T + 31) / 32;
+  for (int c = 0; c < n_chunks; ++c) {
+    const int t = c * 32 + lane;
+    bool kept = false;
+    if (t + 1 < T && flagged.get(t)) {
+      const Mask128 below = mask_below(t), upto = mask_below(t + 1);
+      const Mask128 zb = {clear.lo & below.lo, clear.hi & below.hi};
+      const Mask128 za = {clear.lo & ~upto.lo, clear.hi & ~upto.hi};
+      const int a = zb.any() ? mask_msb(zb) + 1 : 0;   // first window of the run
+      const int b = mask_lsb(za) - 1;                   // last window of the run
+      const bool long_enough = (pts[b + 1] - pts[a]) > 0.2;
+      kept = long_enough && (b != last_flag || b > a);
     }
+    const unsigned k32 = __ballot_sync(0xffffffffu, kept);
+    const unsigned pts32 = k32 | (k32 << 1) | carry;
+    carry = k32 >> 31;
+    if (c < 2) m.lo |= (unsigned long long)pts32 << (32 * c);
+    else m.hi |= (unsigned long long)pts32 << (32 * (c - 2));
   }
   return m;
 }
@@ -171,16 +195,16 @@ __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* con
     flags = 0; common = 0.01; mode[0] = 2; mode[1] = 2;
   } else if (zr) {
     flags = 1; common = min_sd[1] / 10.0; mode[0] = 2;
-    mask[1] = region_mask(flagged[1], T, p.points);
+    mask[1] = region_mask(flagged[1], T, p.points, lane);
     if (mask[1].any()) { mode[1] = 1; flags |= G2G_FLAG_REGION_QUERY; }
   } else if (zq) {
     flags = 2; common = min_sd[0] / 10.0; mode[1] = 2;
-    mask[0] = region_mask(flagged[0], T, p.points);
+    mask[0] = region_mask(flagged[0], T, p.points, lane);
     if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
   } else {
     flags = 3;
-    mask[0] = region_mask(flagged[0], T, p.points);
-    mask[1] = region_mask(flagged[1], T, p.points);
+    mask[0] = region_mask(flagged[0], T, p.points, lane);
+    mask[1] = region_mask(flagged[1], T, p.points, lane);
     if (mask[0].any() || mask[1].any()) {
       common = fmin(min_sd[0], min_sd[1]) / 10.0;
       if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
