@@ -229,3 +229,45 @@ def test_average_alignment_walk_matches_reference(golden_dir):
         S, T = Main.matched_time_points(str(ref["alignment_str"][g]))
         np.add.at(mat, (T + 1, S + 1), 1)
     assert np.array_equal(mat, ref["match_count_mat"])
+
+
+def _region_mask_bit_scan(flagged, T, pts):
+    """Python restatement of the kernel's formulation (csrc/g2g_fixup_body.cuh region_mask): every
+    flagged window finds the bounds [a, b] of its run with bit scans, decides `keep`, and point t is
+    listed iff window t or window t-1 lies in a kept run."""
+    if flagged == 0:
+        return 0
+    last = flagged.bit_length() - 1
+    full = (1 << 128) - 1
+    kept = 0
+    for t in range(T - 1):
+        if (flagged >> t) & 1:
+            zb = ~flagged & ((1 << t) - 1)
+            a = zb.bit_length() if zb else 0
+            za = ~flagged & full & ~((1 << (t + 1)) - 1)
+            b = (za & -za).bit_length() - 2
+            if (pts[b + 1] - pts[a]) > 0.2 and (b != last or b > a):
+                kept |= 1 << t
+    return (kept | (kept << 1)) & full
+
+
+def test_region_mask_formulation_equals_the_reference_run_walk():
+    """The lane-parallel region mask of the fix-up kernel against the oracle's restatement of
+    extract_significant_regions_only (Main.py:261-291) + np.in1d(points, regions): exhaustive over all
+    flag patterns for short series, random patterns up to 128 points."""
+    import random
+    rng = random.Random(7)
+    for T in (2, 3, 5, 7, 13, 14, 29, 50, 64, 65, 100, 128):
+        pts = np.linspace(0, 1, T)
+        if T <= 14:
+            patterns = range(1 << (T - 1))
+        else:
+            patterns = []
+            for _ in range(600):
+                dens = rng.choice([0.1, 0.5, 0.9, 0.98])
+                patterns.append(sum(1 << k for k in range(T - 1) if rng.random() < dens))
+        for f in patterns:
+            regions = [[pts[k], pts[k + 1]] for k in range(T - 1) if (f >> k) & 1]
+            listed = o.extract_significant_regions_only(regions)
+            want = sum(1 << int(t) for t in np.nonzero(np.isin(pts, listed))[0])
+            assert _region_mask_bit_scan(f, T, pts) == want, (T, bin(f))
