@@ -130,6 +130,9 @@ constexpr int kMaxChunks = G2G_MAX_BINS / 32;
 // One warp finishes one gene; lanes run over the interpolation points.  `tot_f64[s]` / `tot_i32[s]` hold the
 // split totals of side s as [row][gs] arrays, the gene at column `gi` (global memory for the stand-alone
 // kernel, shared memory in the fused one); `g` is the gene's index in pilot[] and the outputs.
+// NCH = compile-time bound on the number of 32-point chunks (ceil(T / 32) <= NCH): the callers that know
+// it (the fused kernel, per DP column count) get correspondingly less code.
+template <int NCH = kMaxChunks>
 __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* const* tot_f64,
                                            const int32_t* const* tot_i32, long long gs, long long gi, long long g,
                                            int lane) {
@@ -137,7 +140,7 @@ __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* con
   const int n_chunks = (T + 31) / 32;
   const double inf = __longlong_as_double(0x7ff0000000000000LL);
 
-  double mean[2][kMaxChunks], sd[2][kMaxChunks], min_sd[2];
+  double mean[2][NCH], sd[2][NCH], min_sd[2];
   int nz[2];
   Mask128 flagged[2];
 #pragma unroll
@@ -150,7 +153,7 @@ __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* con
     int cnt = 0;
     flagged[sd_i].lo = flagged[sd_i].hi = 0ull;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       mean[sd_i][c] = 0.0;
       sd[sd_i][c] = inf;
       if (c < n_chunks) {
@@ -191,20 +194,20 @@ __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* con
   int mode[2] = {0, 0};
   Mask128 mask[2] = {{0ull, 0ull}, {0ull, 0ull}};
   const bool zr = nz[0] <= 3, zq = nz[1] <= 3;
+  // a side's low-expression regions matter exactly when that side is expressed (one call site per side
+  // keeps the code small; zr / zq are warp-uniform)
+  if (!zr) mask[0] = region_mask(flagged[0], T, p.points, lane);
+  if (!zq) mask[1] = region_mask(flagged[1], T, p.points, lane);
   if (zr && zq) {
     flags = 0; common = 0.01; mode[0] = 2; mode[1] = 2;
   } else if (zr) {
     flags = 1; common = min_sd[1] / 10.0; mode[0] = 2;
-    mask[1] = region_mask(flagged[1], T, p.points, lane);
     if (mask[1].any()) { mode[1] = 1; flags |= G2G_FLAG_REGION_QUERY; }
   } else if (zq) {
     flags = 2; common = min_sd[0] / 10.0; mode[1] = 2;
-    mask[0] = region_mask(flagged[0], T, p.points, lane);
     if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
   } else {
     flags = 3;
-    mask[0] = region_mask(flagged[0], T, p.points, lane);
-    mask[1] = region_mask(flagged[1], T, p.points, lane);
     if (mask[0].any() || mask[1].any()) {
       common = fmin(min_sd[0], min_sd[1]) / 10.0;
       if (mask[0].any()) { mode[0] = 1; flags |= G2G_FLAG_REGION_REF; }
@@ -218,7 +221,7 @@ __device__ __forceinline__ void fixup_gene(const FixParams& p, const double* con
     double* ms = p.musigma + ((size_t)g * 4 + 2 * sd_i) * T;
     double* tr = p.trends + ((size_t)g * 4 + 2 * sd_i) * T;
 #pragma unroll
-    for (int c = 0; c < kMaxChunks; ++c) {
+    for (int c = 0; c < NCH; ++c) {
       const int t = c * 32 + lane;
       if (c < n_chunks && t < T) {
         double m = mean[sd_i][c], s = sd[sd_i][c];

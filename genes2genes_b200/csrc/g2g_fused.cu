@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(kWarpsPerBlock * (32 / LW) * 32) fixup_dp_kern
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double* tf[2] = {tot_f, tot_f + (size_t)rows_f * GPC};
   const int32_t* ti[2] = {tot_i, tot_i + (size_t)T * GPC};
-  if (g0 + warp < q.fix.n_genes) fixup_gene(q.fix, tf, ti, GPC, warp, g0 + warp, lane);
+  if (g0 + warp < q.fix.n_genes) fixup_gene<(B < kMaxChunks ? B : kMaxChunks)>(q.fix, tf, ti, GPC, warp, g0 + warp, lane);
   __syncthreads();   // trends are visible to the block; the DP scratch below reuses the totals' shared memory
   if (warp < kWarpsPerBlock) dp_genes<B, false, LW>(q.dp, smem_raw);
 }
