@@ -692,6 +692,7 @@ class RefQueryAligner:
         ``n_processes`` are accepted for signature compatibility; the batch already runs all genes
         concurrently on the GPU."""
         self._say("Running gene-level alignment: \U0001F9EC")
+        by_gene = None
         if self._dist is not None:
             self._run_batch()                                   # rank 0's gene_list grows to all genes here
             store = self._store
@@ -699,14 +700,17 @@ class RefQueryAligner:
         else:
             # the result objects are O(1) views: build them while the GPU is still working
             store = self._new_store(None)
-            built = []
-            self._run_batch(on_enqueued=lambda: built.extend(
-                AligmentObj(store, k, g) for k, g in enumerate(self.gene_list)), store=store)
+            built, by_gene = [], {}
+
+            def build_views():
+                built.extend(AligmentObj(store, k, g) for k, g in enumerate(self.gene_list))
+                by_gene.update((a.gene, a) for a in built)
+            self._run_batch(on_enqueued=build_views, store=store)
             self.results = built
         text, lens, stride = _string_table(store)
         for k, a in enumerate(self.results):                    # strings are cheap to cut here, dear to cut lazily
             a.alignment_str = text[k * stride:k * stride + lens[k]]
-        self.results_map = {a.gene: a for a in self.results}
+        self.results_map = by_gene if by_gene is not None else {a.gene: a for a in self.results}
         self._say("Alignment completed! ✅")
 
     def compute_DE_info(self):

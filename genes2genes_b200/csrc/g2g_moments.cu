@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   for (int k = tid; k < p.n_bins * C::GT; k += kThreads) cnt_s[k] = 0;
-  __syncthreads();
+  // (no barrier here: thread 0 goes straight on to issue the first loads, the block meets below)
 
   // Load the next tile of this CTA's item sequence into `slot`.  Only one thread runs this at a
   // time: the prologue, then whichever warp finished the previous occupant of the slot last.  The
