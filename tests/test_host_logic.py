@@ -271,3 +271,23 @@ def test_region_mask_formulation_equals_the_reference_run_walk():
             listed = o.extract_significant_regions_only(regions)
             want = sum(1 << int(t) for t in np.nonzero(np.isin(pts, listed))[0])
             assert _region_mask_bit_scan(f, T, pts) == want, (T, bin(f))
+
+
+def test_bench_reference_arm_prints_one_contract_line():
+    """``bench.py --impl reference`` (the CPU arm, no GPU needed): exactly one line on stdout, JSON, with
+    the keys of the measurement contract; library chatter must not reach stdout."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0", "--cpu-genes", "4", "--workload", "C1"],
+                         capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better",
+                "scaling", "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["impl"] == "reference" and d["metric"] == "gene_alignments_per_sec" and d["unit"] == "genes/s"
+    assert d["higher_is_better"] is True and d["value"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
