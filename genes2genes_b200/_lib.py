@@ -24,7 +24,12 @@ class Layout(ctypes.Structure):
 
 class Side(ctypes.Structure):
     _fields_ = [("X", c_vp), ("n_cells", c_i64), ("ldx", c_i64), ("wtab", c_vp), ("pilot", c_vp),
-                ("part_f64", c_vp), ("part_i32", c_vp)]
+                ("part_f64", c_vp), ("part_i32", c_vp), ("n_split", c_i64)]
+
+
+class MmaLayout(ctypes.Structure):
+    _fields_ = [("n_groups", c_i32), ("bins_per_group", c_i32), ("n_cols", c_i32), ("reserved", c_i32),
+                ("n_pad", c_i64), ("cells_per_item", c_i64), ("n_split", c_i64), ("table_bytes", c_i64)]
 
 
 class SparseSide(ctypes.Structure):
@@ -40,10 +45,15 @@ SIGNATURES = {
     "g2g_layout": (c_i32, [c_i64, c_i32, ctypes.POINTER(Layout)]),
     "g2g_pack_rows": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_pack_csr": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "g2g_upload_block": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
+    "g2g_scatter_rows": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_weights_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "g2g_weights": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_pilot_mean": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp]),
     "g2g_moments": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp]),
+    "g2g_mma_layout": (c_i32, [c_i64, c_i32, ctypes.POINTER(MmaLayout)]),
+    "g2g_weights_mma": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "g2g_moments_mma": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp, c_vp]),
     "g2g_moments_csc": (c_i32, [ctypes.POINTER(SparseSide), c_i32, c_i64, c_i64, c_i32, c_vp]),
     "g2g_fixup_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "g2g_fixup_trends": (c_i32, [ctypes.POINTER(Side), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32,
@@ -86,6 +96,12 @@ def check(rc, what):
     if rc != 0:
         msg = load().g2g_last_error()
         raise G2GError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def mma_layout(n_cells, n_bins):
+    out = MmaLayout()
+    check(load().g2g_mma_layout(int(n_cells), int(n_bins), ctypes.byref(out)), "g2g_mma_layout")
+    return out
 
 
 def layout(n_cells, n_bins):

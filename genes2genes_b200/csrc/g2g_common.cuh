@@ -46,3 +46,18 @@ static inline G2GTiling g2g_tiling(int n_bins) {
   t.genes_per_thread = t.bins_even <= 28 ? 2 : 1;
   return t;
 }
+
+// Tiling of the tensor-core interpolation kernel (g2g_moments_mma / g2g_weights_mma): bins in groups of
+// <= 64, N = group size rounded up to the MMA granularity of 16.
+struct G2GMmaTiling {
+  int n_groups, bins_per_group, n_cols;
+};
+static inline G2GMmaTiling g2g_mma_tiling(int n_bins) {
+  G2GMmaTiling t;
+  t.n_groups = (int)g2g_ceil_div(n_bins, 64);
+  t.bins_per_group = (int)g2g_ceil_div(n_bins, t.n_groups);
+  t.n_cols = (int)g2g_round_up(t.bins_per_group, 16);
+  return t;
+}
+// bytes of one 64-cell stage of the g2g_weights_mma table: 4 K steps x (hi + lo) x [n_cols x 16] f16 + 64 window words
+__host__ __device__ static inline size_t g2g_mma_stage_bytes(int n_cols) { return (size_t)n_cols * 256 + 256; }

@@ -65,7 +65,7 @@ extern "C" int g2g_fixup_trends(const g2g_side_t* sides, const double* sum_w_ref
     if (rc != G2G_OK) return rc;
     rp.part_f64[s] = sides[s].part_f64;
     rp.part_i32[s] = sides[s].part_i32;
-    rp.n_split[s] = lay.n_split;
+    rp.n_split[s] = sides[s].n_split > 0 ? sides[s].n_split : lay.n_split;
     p.side[s].pilot = sides[s].pilot;
     p.side[s].sum_w = s == 0 ? sum_w_ref : sum_w_query;
     p.side[s].n_cells = sides[s].n_cells;

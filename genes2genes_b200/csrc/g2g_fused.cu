@@ -105,7 +105,7 @@ extern "C" int g2g_fixup_cost_dp(const g2g_side_t* sides, const double* sum_w_re
     q.red.part_i32[s] = sides[s].part_i32;
     q.red.red_f64[s] = nullptr;
     q.red.red_i32[s] = nullptr;
-    q.red.n_split[s] = lay.n_split;
+    q.red.n_split[s] = sides[s].n_split > 0 ? sides[s].n_split : lay.n_split;
     q.fix.side[s].pilot = sides[s].pilot;
     q.fix.side[s].sum_w = s == 0 ? sum_w_ref : sum_w_query;
     q.fix.side[s].n_cells = sides[s].n_cells;

@@ -1,0 +1,581 @@
+// K1m  g2g_moments_mma: the interpolation pass of g2g_moments on the tensor cores (30 <= n_bins).
+//
+//     out[gene][bin] = sum_c  X[c][gene] * W[c][bin]          (TimeSeriesPreprocessor.py:161-174)
+//
+// is a [genes x cells] . [cells x bins] contraction.  Here it runs as tcgen05.mma kind::f16 with M = 128
+// genes (one TMEM lane per gene), N = bins (+ the `valid` column) and K = 16 cells per instruction:
+//
+//   * X tiles [64 cells x 128 genes] f32 arrive by TMA, the matching B operand slice of the weight table
+//     (f16 hi / lo, canonical K-major layout written by g2g_weights_mma) by a bulk copy, into a ring of
+//     kStages shared-memory stages;
+//   * converter warps (thread = gene) read their gene's 16 values of a K step, form y = (x - a)^2 and
+//     split x and y into f16 pairs (hi, lo * 2048) -- 22 significant bits -- which they store to tensor
+//     memory (tcgen05.st) as the A operands; they also count the non-zero values per pseudotime window
+//     and add up x - a (the un-weighted sum needs no tensor core);
+//   * one thread issues six MMAs per K step:  hhA += xh.wh, hhB += yh.wh, loA += xl.wh + xh.wl,
+//     loB += yl.wh + yh.wl  (f32 accumulators in TMEM; the lo.lo product, 2^-22 of the result, is dropped);
+//   * the tensor core truncates when it adds (profiles/r02_umma_ts_probe.txt: -1e-7 of the sum per step),
+//     so the hh chains are cut every kFlushSteps = 16 steps (256 cells): flusher warps read the accumulator
+//     (two buffers alternate) and add it, round to nearest, to f32 registers; at the end of a work item they
+//     add the lo accumulator / 2048 in f64 and write the item's partial sums.
+//
+// The first moment is accumulated un-shifted on purpose: the truncation error is proportional to the sum
+// of the magnitudes added, and only for sum w x is that the bin's own mean (with x - a it would be |a - mean|,
+// which dwarfs the mean of a weakly expressed bin).
+// Outputs as g2g_moments, except that there are g2g_mma_layout().n_split planes and that the window
+// counts are added to part_i32 with integer atomics (the call zeroes it first).
+#include "g2g_common.cuh"
+#include <cuda.h>
+#include <cuda_fp16.h>
+
+namespace {
+
+constexpr int kGT = 128;               // genes per tile = TMEM lanes
+constexpr int kStageCells = G2G_CELL_TILE;
+constexpr int kStepCells = 16;         // K of one kind::f16 MMA
+constexpr int kStepsPerStage = kStageCells / kStepCells;
+constexpr int kFlushSteps = 16;        // K steps per first-level accumulation chain
+constexpr int kStages = 4;
+constexpr int kABufs = 4;              // A operand staging buffers in TMEM (32 columns each)
+constexpr int kConvGroups = 2;         // converter groups of 4 warps (one warp per 32 TMEM lanes)
+constexpr int kFlushWarps = 8;         // 2 per lane quarter: A' half and B half of an accumulator buffer
+constexpr int kFirstFlushWarp = 4, kFirstConvWarp = kFirstFlushWarp + kFlushWarps;
+constexpr int kWarps = kFirstConvWarp + 4 * kConvGroups;
+constexpr int kThreads = kWarps * 32;
+constexpr int kXBytes = kStageCells * kGT * 4;
+constexpr int kMaxSides = 2;
+constexpr float kLoScale = 2048.0f;
+
+struct MmaSide {
+  const unsigned char* table;   // [n_groups][n_pad/64] stages
+  const float* pilot;
+  double* part_f64;
+  int32_t* part_i32;
+  long long n_pad, cells_per_item, n_cells;
+  int n_split, item_base;
+};
+
+struct MmaParams {
+  CUtensorMap tmap[kMaxSides];
+  MmaSide side[kMaxSides];
+  long long n_genes, g_stride;
+  int32_t* status;
+  int n_sides, n_bins, n_groups, bins_per_group, n_gtiles, n_items;
+};
+
+struct Item {
+  int side, bg, split, gt, n_tiles;
+  long long row0;
+};
+
+__device__ __forceinline__ Item decode_item(const MmaParams& p, int item) {
+  Item it;
+  it.side = (p.n_sides > 1 && item >= p.side[1].item_base) ? 1 : 0;
+  const MmaSide& s = p.side[it.side];
+  int r = item - s.item_base;
+  it.gt = r % p.n_gtiles;
+  r /= p.n_gtiles;
+  it.split = r % s.n_split;
+  it.bg = r / s.n_split;
+  it.row0 = (long long)it.split * s.cells_per_item;
+  long long rows = s.n_pad - it.row0;
+  if (rows > s.cells_per_item) rows = s.cells_per_item;
+  it.n_tiles = (int)(rows / kStageCells);
+  return it;
+}
+
+// ---- PTX helpers ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(v[0]),
+               "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]   (M = 128, kind::f16, f32 accumulate)
+__device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+// the mbarrier gets one arrival when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// shared-memory matrix descriptor: K-major, no swizzle (8-row x 16-byte core matrices, rows 16 B apart);
+// LBO = distance of the two 16-byte K chunks of a K = 16 step, SBO = distance of consecutive 8-row blocks
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | ((uint64_t)1 << 46);
+}
+// instruction descriptor: D = f32 (bit 4), A = B = f16 (0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+__device__ __forceinline__ uint32_t instr_desc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+#ifdef __CUDA_FTZ
+#error "g2g_moments_mma.cu must be compiled without -ftz=true / --use_fast_math: nonzero_flag() relies on f32 denormals"
+#endif
+__device__ __forceinline__ int nonzero_flag(float x) { return __float_as_int(fminf(fabsf(x), __int_as_float(1))); }
+
+// Shared memory: [kStages][X tile 32 KB | B slice N*256 | 64 window words] | barriers
+template <int N>
+struct Smem {
+  static constexpr int kBBytes = N * 256 + 256;            // = g2g_mma_stage_bytes(N)
+  static constexpr int kStageBytes = kXBytes + kBBytes;
+  static constexpr int kBarOffset = kStages * kStageBytes;
+  static constexpr int kTotal = kBarOffset + 256 + 2 * kConvGroups * kGT * 8;
+};
+
+template <int N>
+__global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_constant__ MmaParams p) {
+  using S = Smem<N>;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBarOffset);
+  uint64_t* stage_full = bars;                       // [kStages]  TMA bytes landed
+  uint64_t* stage_empty = stage_full + kStages;      // [kStages]  MMAs of the stage's 4 steps done
+  uint64_t* a_full = stage_empty + kStages;          // [kABufs]   converters wrote the A operands (4 warps)
+  uint64_t* a_empty = a_full + kABufs;               // [kABufs]   MMAs that read them done
+  uint64_t* acc_full = a_empty + kABufs;             // [2]        a 256-cell chain is complete
+  uint64_t* acc_empty = acc_full + 2;                // [2]        flushers have read it (kFlushWarps)
+  uint64_t* lo_full = acc_empty + 2;                 // [1]        item complete
+  uint64_t* lo_empty = lo_full + 1;                  // [1]
+  uint64_t* done_bar = lo_empty + 1;                 // [1]        every MMA (and commit) of this CTA has retired
+  uint64_t* c_full = done_bar + 1;                   // [2]        converters posted an item's sum (x - a)
+  uint64_t* c_empty = c_full + 2;                    // [2]        flushers took it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(c_empty + 2);
+  double* c_s = reinterpret_cast<double*>(smem + S::kBarOffset + 256);   // [2][kConvGroups][kGT]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) { mbar_init(&stage_full[s], 1); mbar_init(&stage_empty[s], 1); }
+    for (int b = 0; b < kABufs; ++b) { mbar_init(&a_full[b], 4); mbar_init(&a_empty[b], 1); }
+    for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 1); mbar_init(&acc_empty[b], kFlushWarps); }
+    mbar_init(lo_full, 1);
+    mbar_init(lo_empty, kFlushWarps);
+    mbar_init(done_bar, 1);
+    for (int b = 0; b < 2; ++b) { mbar_init(&c_full[b], 4 * kConvGroups); mbar_init(&c_empty[b], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  // TMEM columns: accumulator buffer b: [b*2N, b*2N + N) = A' (first moment), [.. + N, .. + 2N) = B (second);
+  // lo accumulators at 4N (A') and 5N (B); A operand staging buffers of 32 columns from 6N
+  constexpr uint32_t kLoCol = 4 * N, kACol = 6 * N;
+  static_assert(kACol + 32 * kABufs <= 512, "TMEM columns");
+
+  if (warp == 0) {
+    // ================= producer: TMA loads of the X tiles, bulk copies of the B slices ==================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const Item it = decode_item(p, item);
+        const MmaSide& s = p.side[it.side];
+        const size_t n_stage_rows = (size_t)(s.n_pad / kStageCells);
+        for (int tile = 0; tile < it.n_tiles; ++tile) {
+          mbar_wait(&stage_empty[stage], ph ^ 1);
+          unsigned char* dst = smem + (size_t)stage * S::kStageBytes;
+          const long long row = it.row0 + (long long)tile * kStageCells;
+          mbar_arrive_expect_tx(&stage_full[stage], S::kStageBytes);
+          tma_load_2d(dst, &p.tmap[it.side], it.gt * kGT, (int)row, &stage_full[stage]);
+          bulk_load_1d(dst + kXBytes, s.table + ((size_t)it.bg * n_stage_rows + (size_t)(row / kStageCells)) * S::kBBytes,
+                       S::kBBytes, &stage_full[stage]);
+          if (++stage == kStages) { stage = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer ========================================================================
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc(kGT, N);
+      int stage = 0;
+      uint32_t sph = 0;
+      uint32_t n_step = 0, n_chain = 0, n_item = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
+        const Item it = decode_item(p, item);
+        const int total = it.n_tiles * kStepsPerStage;
+        mbar_wait(lo_empty, (n_item & 1) ^ 1);
+        int ks = 0;
+        for (int tile = 0; tile < it.n_tiles; ++tile) {
+          mbar_wait(&stage_full[stage], sph);
+          const uint32_t b_base = smem_u32(smem + (size_t)stage * S::kStageBytes + kXBytes);
+#pragma unroll 1
+          for (int s4 = 0; s4 < kStepsPerStage; ++s4, ++ks, ++n_step) {
+            const uint32_t accb = n_chain & 1;
+            const int in_chain = ks % kFlushSteps;
+            if (in_chain == 0) mbar_wait(&acc_empty[accb], ((n_chain >> 1) & 1) ^ 1);
+            const uint32_t ab = n_step % kABufs;
+            mbar_wait(&a_full[ab], (n_step / kABufs) & 1);
+            tc_fence_after();
+            const uint64_t d_hi = smem_desc(b_base + s4 * (N * 64), N * 16, 128);
+            const uint64_t d_lo = smem_desc(b_base + s4 * (N * 64) + N * 32, N * 16, 128);
+            const uint32_t a0 = tbase + kACol + ab * 32;      // xh | xl | yh | yl, 8 columns each
+            const uint32_t hh = tbase + accb * (2 * N);
+            const uint32_t lo = tbase + kLoCol;
+            umma_ts(hh, a0, d_hi, idesc, in_chain > 0);
+            umma_ts(hh + N, a0 + 16, d_hi, idesc, in_chain > 0);
+            umma_ts(lo, a0 + 8, d_hi, idesc, ks > 0);
+            umma_ts(lo, a0, d_lo, idesc, 1);
+            umma_ts(lo + N, a0 + 24, d_hi, idesc, ks > 0);
+            umma_ts(lo + N, a0 + 16, d_lo, idesc, 1);
+            umma_commit(&a_empty[ab]);
+            const bool last = ks + 1 == total;
+            if (in_chain == kFlushSteps - 1 || last) {
+              umma_commit(&acc_full[accb]);
+              ++n_chain;
+            }
+            if (last) umma_commit(lo_full);
+          }
+          umma_commit(&stage_empty[stage]);
+          if (++stage == kStages) { stage = 0; sph ^= 1; }
+        }
+      }
+      // no barrier arrival of this CTA may still be in flight when its shared memory is released
+      umma_commit(done_bar);
+      mbar_wait(done_bar, 0);
+    }
+  } else if (warp >= kFirstFlushWarp && warp < kFirstConvWarp) {
+    // ================= flushers: TMEM accumulators -> f32 registers (RN) -> f64 partial sums ============
+    const int q = warp & 3, h = (warp - kFirstFlushWarp) >> 2;   // lane quarter, half (0: A', 1: B)
+    const uint32_t lane_base = tbase + ((uint32_t)(q * 32) << 16);
+    const int T = p.n_bins, TB = p.bins_per_group;
+    float acc[N];
+    uint32_t n_chain = 0, n_item = 0;
+    bool bad = false;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++n_item) {
+      const Item it = decode_item(p, item);
+      const int total = it.n_tiles * kStepsPerStage;
+      const int chains = (total + kFlushSteps - 1) / kFlushSteps;
+#pragma unroll
+      for (int j = 0; j < N; ++j) acc[j] = 0.0f;
+      for (int c = 0; c < chains; ++c, ++n_chain) {
+        const uint32_t accb = n_chain & 1;
+        mbar_wait(&acc_full[accb], (n_chain >> 1) & 1);
+        tc_fence_after();
+        const uint32_t src = lane_base + accb * (2 * N) + h * N;
+#pragma unroll
+        for (int j = 0; j < N; j += 8) {
+          uint32_t v[8];
+          tmem_ld8(src + j, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 8; ++e) acc[j + e] += __uint_as_float(v[e]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&acc_empty[accb]);
+      }
+      // item end: add the lo accumulator, write the f64 partial sums of this (item, gene)
+      mbar_wait(lo_full, n_item & 1);
+      tc_fence_after();
+      const MmaSide& s = p.side[it.side];
+      const long long g = (long long)it.gt * kGT + q * 32 + lane;
+      double* pf = s.part_f64 + (size_t)it.split * (2 * T + 1) * p.g_stride + g;
+#pragma unroll
+      for (int j = 0; j < N; j += 8) {
+        uint32_t v[8];
+        tmem_ld8(lane_base + kLoCol + h * N + j, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = j + e;
+          const double val = (double)acc[col] + (double)__uint_as_float(v[e]) * (1.0 / kLoScale);
+          const int t = it.bg * TB + col;
+          if (col < TB && t < T && g < p.n_genes) {
+            pf[(size_t)(h * T + t) * p.g_stride] = val;
+            if (!isfinite(val)) bad = true;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(lo_empty);
+      if (h == 0) {   // sum (x - a): the converter groups' shares, added in group order
+        const uint32_t par = n_item & 1;
+        mbar_wait(&c_full[par], (n_item >> 1) & 1);
+        double c = 0.0;
+#pragma unroll
+        for (int k = 0; k < kConvGroups; ++k) c += c_s[(par * kConvGroups + k) * kGT + q * 32 + lane];
+        if (it.bg == 0 && g < p.n_genes) pf[(size_t)(2 * T) * p.g_stride] = c;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_empty[par]);
+      }
+    }
+    if (bad) atomicOr(p.status, 1);
+  } else if (warp >= kFirstConvWarp) {
+    // ================= converters: x -> (dh, dl, yh, yl) in tensor memory, window counts ================
+    const int cg = (warp - kFirstConvWarp) >> 2, q = warp & 3;
+    const int gl = q * 32 + lane;
+    const uint32_t lane_base = tbase + ((uint32_t)(q * 32) << 16);
+    const int T = p.n_bins;
+    int stage = 0;
+    uint32_t sph = 0, n_step = 0, n_item = 0;
+    float a_next = 0.0f;
+    {
+      if ((int)blockIdx.x < p.n_items) {
+        const Item nx = decode_item(p, blockIdx.x);
+        const long long g = (long long)nx.gt * kGT + gl;
+        a_next = g < p.n_genes ? p.side[nx.side].pilot[g] : 0.0f;
+      }
+    }
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const Item it = decode_item(p, item);
+      const MmaSide& s = p.side[it.side];
+      const long long g = (long long)it.gt * kGT + gl;
+      const float a = a_next;
+      if (item + (int)gridDim.x < p.n_items) {
+        const Item nx = decode_item(p, item + gridDim.x);
+        const long long gn = (long long)nx.gt * kGT + gl;
+        a_next = gn < p.n_genes ? p.side[nx.side].pilot[gn] : 0.0f;
+      }
+      const bool do_counts = it.bg == 0 && g < p.n_genes;
+      int32_t* pi = s.part_i32 + (size_t)it.split * T * p.g_stride + g;
+      int cur_win = 0, cnt = 0;   // window word: id + 1 (0 = padding rows)
+      double c_acc = 0.0;         // this thread's share of sum (x - a) over the item
+      const long long n_cells = s.n_cells;
+      auto flush_counts = [&]() {
+        if (do_counts && cur_win > 0 && cnt) atomicAdd(pi + (size_t)(cur_win - 1) * p.g_stride, cnt);
+        cnt = 0;
+      };
+      for (int tile = 0; tile < it.n_tiles; ++tile) {
+        bool waited = false;
+        const unsigned char* st = smem + (size_t)stage * S::kStageBytes;
+        const float* xt = reinterpret_cast<const float*>(st);
+        const int* win = reinterpret_cast<const int*>(st + kXBytes + N * 256);
+#pragma unroll 1
+        for (int s4 = 0; s4 < kStepsPerStage; ++s4, ++n_step) {
+          if ((int)(n_step % kConvGroups) != cg) continue;
+          if (!waited) { mbar_wait(&stage_full[stage], sph); waited = true; }
+          const float* xs = xt + (s4 * kStepCells) * kGT + gl;
+          uint32_t xh[8], xl[8], yh[8], yl[8];
+          int nz = 0;
+          float csum = 0.0f;
+          const long long step_row = it.row0 + (long long)tile * kStageCells + s4 * kStepCells;
+          const bool all_valid = step_row + kStepCells <= n_cells;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float x0 = xs[(2 * j) * kGT], x1 = xs[(2 * j + 1) * kGT];
+            nz += nonzero_flag(x0) + nonzero_flag(x1);
+            const float d0 = x0 - a, d1 = x1 - a;
+            const float y0 = d0 * d0, y1 = d1 * d1;
+            csum += d0 + d1;
+            xh[j] = cvt_f16x2(x0, x1);
+            yh[j] = cvt_f16x2(y0, y1);
+            const float2 xhf = unpack_f16x2(xh[j]), yhf = unpack_f16x2(yh[j]);
+            xl[j] = cvt_f16x2((x0 - xhf.x) * kLoScale, (x1 - xhf.y) * kLoScale);
+            yl[j] = cvt_f16x2((y0 - yhf.x) * kLoScale, (y1 - yhf.y) * kLoScale);
+          }
+          if (!all_valid) {   // last step of a dataset: rows past n_cells are zero filled, leave them out
+            csum = 0.0f;
+            for (int c = 0; c < kStepCells; ++c)
+              if (step_row + c < n_cells) csum += xs[c * kGT] - a;
+          }
+          c_acc += (double)csum;
+          // window counts (uniform per step except at the few steps a window boundary falls into)
+          const int w0 = win[s4 * kStepCells];
+          if (!(w0 & G2G_WIN_MIXED)) {
+            if (w0 != cur_win) { flush_counts(); cur_win = w0; }
+            cnt += nz;
+          } else {
+            for (int c = 0; c < kStepCells; ++c) {
+              const int w = win[s4 * kStepCells + c] & (G2G_WIN_MIXED - 1);
+              if (w != cur_win) { flush_counts(); cur_win = w; }
+              cnt += nonzero_flag(xs[c * kGT]);
+            }
+          }
+          const uint32_t ab = n_step % kABufs;
+          mbar_wait(&a_empty[ab], ((n_step / kABufs) & 1) ^ 1);
+          tc_fence_after();
+          const uint32_t dst = lane_base + kACol + ab * 32;
+          tmem_st8(dst, xh);
+          tmem_st8(dst + 8, xl);
+          tmem_st8(dst + 16, yh);
+          tmem_st8(dst + 24, yl);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[ab]);
+        }
+        if (++stage == kStages) { stage = 0; sph ^= 1; }
+      }
+      flush_counts();
+      {   // hand this group's share of sum (x - a) to the flushers
+        const uint32_t par = n_item & 1;
+        mbar_wait(&c_empty[par], ((n_item >> 1) & 1) ^ 1);
+        c_s[(par * kConvGroups + cg) * kGT + gl] = c_acc;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&c_full[par]);
+      }
+      ++n_item;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tbase, 512);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int get_encode_fn(EncodeTiledFn* out) {
+  static EncodeTiledFn cached = nullptr;
+  if (!cached) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    G2G_CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+      g2g_set_error("cuTensorMapEncodeTiled not available from the driver");
+      return G2G_ERR_CUDA;
+    }
+    cached = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  *out = cached;
+  return G2G_OK;
+}
+
+template <int N>
+int launch_mma(MmaParams& p, const g2g_side_t* sides, cudaStream_t stream) {
+  EncodeTiledFn encode;
+  int rc = get_encode_fn(&encode);
+  if (rc != G2G_OK) return rc;
+  for (int s = 0; s < p.n_sides; ++s) {
+    cuuint64_t gdim[2] = {(cuuint64_t)p.n_genes, (cuuint64_t)sides[s].n_cells};
+    cuuint64_t gstride[1] = {(cuuint64_t)sides[s].ldx * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)kGT, (cuuint32_t)kStageCells};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = encode(&p.tmap[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(sides[s].X), gdim,
+                        gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      g2g_set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+      return G2G_ERR_CUDA;
+    }
+  }
+  p.n_gtiles = (int)g2g_ceil_div(p.n_genes, kGT);
+  int items = 0;
+  for (int s = 0; s < p.n_sides; ++s) {
+    p.side[s].item_base = items;
+    items += p.n_groups * p.side[s].n_split * p.n_gtiles;
+  }
+  p.n_items = items;
+  int dev = 0, n_sm = 0;
+  G2G_CUDA_TRY(cudaGetDevice(&dev));
+  G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
+  const size_t smem = Smem<N>::kTotal;
+  G2G_CUDA_TRY(cudaFuncSetAttribute(moments_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int grid = n_sm;   // one CTA per SM: the kernel owns all 512 TMEM columns
+  if (grid > items) grid = items;
+  moments_mma_kernel<N><<<grid, kThreads, smem, stream>>>(p);
+  G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+
+}  // namespace
+
+extern "C" int g2g_moments_mma(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                               int32_t n_bins, int32_t* status, void* stream) {
+  G2G_REQUIRE(sides != nullptr && n_sides >= 1 && n_sides <= kMaxSides, "n_sides must be 1 or 2");
+  G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
+  G2G_REQUIRE(n_genes >= 1 && g_stride >= n_genes, "bad gene counts");
+  G2G_REQUIRE(n_genes < (1ll << 31), "n_genes too large");
+  G2G_REQUIRE(status != nullptr, "null status pointer");
+  G2GMmaTiling t = g2g_mma_tiling(n_bins);
+  MmaParams p;
+  p.n_genes = n_genes; p.g_stride = g_stride; p.n_sides = n_sides; p.n_bins = n_bins; p.n_groups = t.n_groups;
+  p.bins_per_group = t.bins_per_group;
+  p.status = status;
+  cudaStream_t st = (cudaStream_t)stream;
+  for (int s = 0; s < n_sides; ++s) {
+    const g2g_side_t& in = sides[s];
+    G2G_REQUIRE(in.X && in.wtab && in.pilot && in.part_f64 && in.part_i32, "null pointer in side");
+    G2G_REQUIRE(in.n_cells >= 1 && in.n_cells < (1ll << 31), "n_cells out of range");
+    G2G_REQUIRE(in.ldx >= n_genes && in.ldx % 4 == 0, "ldx must be >= n_genes and a multiple of 4 (16-byte rows for TMA)");
+    G2G_REQUIRE(((uintptr_t)in.X & 15) == 0, "X must be 16-byte aligned");
+    G2G_REQUIRE(((uintptr_t)in.wtab & 127) == 0, "the weight table must be 128-byte aligned");
+    g2g_mma_layout_t lay;
+    int rc = g2g_mma_layout(in.n_cells, n_bins, &lay);
+    if (rc != G2G_OK) return rc;
+    p.side[s].table = reinterpret_cast<const unsigned char*>(in.wtab);
+    p.side[s].pilot = in.pilot;
+    p.side[s].part_f64 = in.part_f64; p.side[s].part_i32 = in.part_i32;
+    p.side[s].n_pad = lay.n_pad; p.side[s].cells_per_item = lay.cells_per_item;
+    p.side[s].n_split = (int)lay.n_split;
+    p.side[s].n_cells = in.n_cells;
+    G2G_CUDA_TRY(cudaMemsetAsync(in.part_i32, 0, (size_t)lay.n_split * n_bins * g_stride * sizeof(int32_t), st));
+  }
+  switch (t.n_cols) {
+    case 16: return launch_mma<16>(p, sides, st);
+    case 32: return launch_mma<32>(p, sides, st);
+    case 48: return launch_mma<48>(p, sides, st);
+    case 64: return launch_mma<64>(p, sides, st);
+    default:
+      g2g_set_error("n_cols %d has no compiled kernel", t.n_cols);
+      return G2G_ERR_UNSUPPORTED;
+  }
+}

@@ -10,12 +10,13 @@ namespace {
 __global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ src, long long n_cells,
                                                         long long n_genes, long long ld_src,
                                                         const long long* __restrict__ row_order,
+                                                        const long long* __restrict__ dst_row,
                                                         const int* __restrict__ gene_idx, float* __restrict__ dst,
                                                         long long ld_dst) {
   const long long r = blockIdx.y;
   const long long sr = row_order ? row_order[r] : r;
   const float* in = src + (size_t)sr * ld_src;
-  float* out = dst + (size_t)r * ld_dst;
+  float* out = dst + (size_t)(dst_row ? dst_row[r] : r) * ld_dst;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < ld_dst;
        g += (long long)gridDim.x * blockDim.x) {
     float v = 0.0f;
@@ -60,10 +61,39 @@ extern "C" int g2g_pack_rows(const float* src, int64_t n_cells, int64_t n_genes,
     dim3 grid(bx, (unsigned)rows);
     pack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         src, rows, n_genes, ld_src, row_order ? reinterpret_cast<const long long*>(row_order) + r0 : nullptr,
-        gene_idx, dst + (size_t)r0 * ld_dst, ld_dst);
+        nullptr, gene_idx, dst + (size_t)r0 * ld_dst, ld_dst);
     if (!row_order) src += (size_t)rows * ld_src;
   }
   G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+
+extern "C" int g2g_scatter_rows(const float* src, int64_t n_rows, int64_t n_genes, int64_t ld_src,
+                                const int64_t* dst_row, const int32_t* gene_idx, float* dst, int64_t ld_dst,
+                                void* stream) {
+  G2G_REQUIRE(src && dst && dst_row, "null pointer");
+  G2G_REQUIRE(n_rows >= 1 && n_genes >= 1 && ld_dst >= n_genes, "bad shape");
+  unsigned bx = (unsigned)g2g_ceil_div(ld_dst, 256);
+  if (bx > 64) bx = 64;
+  for (int64_t r0 = 0; r0 < n_rows; r0 += 65535) {
+    int64_t rows = n_rows - r0 < 65535 ? n_rows - r0 : 65535;
+    dim3 grid(bx, (unsigned)rows);
+    pack_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(src + (size_t)r0 * ld_src, rows, n_genes, ld_src, nullptr,
+                                                             reinterpret_cast<const long long*>(dst_row) + r0,
+                                                             gene_idx, dst, ld_dst);
+  }
+  G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+
+extern "C" int g2g_upload_block(const float* host_src, int64_t ld_src, int64_t row0, int64_t n_rows, int64_t col0,
+                                int64_t n_cols, float* dst, int64_t ld_dst, void* stream) {
+  G2G_REQUIRE(host_src && dst, "null pointer");
+  G2G_REQUIRE(n_rows >= 1 && n_cols >= 1 && row0 >= 0 && col0 >= 0, "bad block");
+  G2G_REQUIRE(ld_src >= col0 + n_cols && ld_dst >= n_cols, "block does not fit the leading dimensions");
+  G2G_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ld_dst * sizeof(float), host_src + (size_t)row0 * ld_src + col0,
+                                 (size_t)ld_src * sizeof(float), (size_t)n_cols * sizeof(float), (size_t)n_rows,
+                                 cudaMemcpyHostToDevice, (cudaStream_t)stream));
   return G2G_OK;
 }
 

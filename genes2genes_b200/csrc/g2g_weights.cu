@@ -1,6 +1,7 @@
 // K0  g2g_weights     Gaussian-kernel weight table + per-bin weight sums for one dataset
 // K1a g2g_pilot_mean  per-gene shift value from a fixed strided row sample
 #include "g2g_common.cuh"
+#include <cuda_fp16.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -18,6 +19,8 @@ struct WeightsParams {
   unsigned int* counter;  // zeroed by the launcher
   long long n_cells, n_pad;
   int n_bins, n_groups, bins_per_group, bins_even, row_floats;
+  unsigned char* mma_table;   // kMma: [n_groups][n_pad / 64] stages of g2g_mma_stage_bytes(n_cols) bytes
+  int n_cols;                 // kMma: N of the MMA (bins_per_group + 1 rounded up to 16)
 };
 
 constexpr int kWCells = 64;                 // cells per block
@@ -27,6 +30,13 @@ constexpr int kWLanes = kWThreads / kWCells;  // threads per cell, striding over
 // rounded once to float32 for the table.  Block = 64 cells x 4 bin lanes.  The per-bin sums of the
 // f64 weights are reduced in a fixed order: 16-cell partial sums, then 4 partials per block, then
 // (last block to finish) the blocks in index order.
+//
+// kMma = true writes the table of the tensor-core kernel instead (g2g_moments_mma): per bin group and
+// 64-cell stage, for each of the four 16-cell K steps the f16 B operand [n_cols x 16] of w_hi = f16(w) and
+// of w_lo = f16((w - w_hi) * 2048) in the canonical K-major no-swizzle layout (8-row x 16-byte core matrices:
+// element (n, k) at (k/8) * n_cols*16 + (n/8) * 128 + (n%8) * 16 + (k%8) * 2 bytes), then 64 window words
+// (window id + 1, 0 for padding rows, bit 16 set when the 16-cell step spans several windows).
+template <bool kMma>
 __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams p) {
   __shared__ double s_pts[G2G_MAX_BINS];
   __shared__ double s_den[G2G_MAX_BINS];
@@ -54,6 +64,43 @@ __global__ void __launch_bounds__(kWThreads) weights_kernel(const WeightsParams 
     s_w[t][cl] = w;
   }
   __syncthreads();
+  if constexpr (kMma) {
+    const int N = p.n_cols;
+    const size_t stage_bytes = g2g_mma_stage_bytes(N);
+    const size_t n_stages = (size_t)(p.n_pad / kWCells);
+    if ((long long)blockIdx.x * kWCells < p.n_pad) {
+      for (int g = 0; g < p.n_groups; ++g) {
+        unsigned char* st = p.mma_table + ((size_t)g * n_stages + blockIdx.x) * stage_bytes;
+        // one thread per (column n, cell pair): 32 pairs per column
+        for (int idx = threadIdx.x; idx < N * 32; idx += kWThreads) {
+          const int n = idx >> 5, pr = idx & 31, c0 = pr * 2;          // cells c0, c0 + 1 of the stage
+          const int t = g * p.bins_per_group + n;
+          double w[2] = {0.0, 0.0};
+          if (n < p.bins_per_group && t < T) { w[0] = s_w[t][c0]; w[1] = s_w[t][c0 + 1]; }
+          const __half h0 = __double2half(w[0]), h1 = __double2half(w[1]);
+          const __half l0 = __double2half((w[0] - (double)__half2float(h0)) * 2048.0);
+          const __half l1 = __double2half((w[1] - (double)__half2float(h1)) * 2048.0);
+          const int ks = c0 >> 4, k = c0 & 15;
+          const size_t off = (size_t)ks * (N * 64) + (size_t)(k >> 3) * (N * 16) + (size_t)(n >> 3) * 128 +
+                             (size_t)(n & 7) * 16 + (size_t)(k & 7) * 2;
+          *reinterpret_cast<__half2*>(st + off) = __halves2half2(h0, h1);
+          *reinterpret_cast<__half2*>(st + off + N * 32) = __halves2half2(l0, l1);
+        }
+        if (threadIdx.x < kWCells) {   // warps 0, 1: lanes are consecutive cells
+          int win = 0;
+          if (valid) {
+            win = T;   // cells outside every window count at index T - 1
+            for (int k = 0; k + 1 < T; ++k)
+              if (tau >= s_pts[k] && tau < s_pts[k + 1]) win = k + 1;
+          }
+          const unsigned same = __match_any_sync(0xffffffffu, win);
+          const unsigned group = 0xffffu << ((threadIdx.x & 31) & ~15);
+          if ((same & group) != group) win |= G2G_WIN_MIXED;
+          reinterpret_cast<int*>(st + (size_t)N * 256)[threadIdx.x] = win;
+        }
+      }
+    }
+  } else
   // table rows: [w_0 .. w_{TB-1}, (zero bin when TB is odd), valid, window id, 0 pad] per group
   if (in_pad) {
     for (int g = 0; g < p.n_groups; ++g) {
@@ -186,30 +233,84 @@ extern "C" size_t g2g_weights_workspace_bytes(int64_t n_cells, int32_t n_bins) {
   return (size_t)blocks * n_bins * sizeof(double) + 16;
 }
 
-extern "C" int g2g_weights(const double* tau, int64_t n_cells, const double* points, const double* denom,
-                           int32_t n_bins, float* wtab, double* sum_w, void* workspace,
-                           size_t workspace_bytes, void* stream) {
-  G2G_REQUIRE(tau && points && denom && wtab && sum_w && workspace, "null pointer");
+namespace {
+int launch_weights(const double* tau, int64_t n_cells, const double* points, const double* denom, int32_t n_bins,
+                   float* wtab, void* mma_table, double* sum_w, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  G2G_REQUIRE(tau && points && denom && (wtab || mma_table) && sum_w && workspace, "null pointer");
   G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
   G2G_REQUIRE(n_cells >= 1, "n_cells must be positive");
   G2G_REQUIRE(workspace_bytes >= g2g_weights_workspace_bytes(n_cells, n_bins), "workspace too small");
   G2G_REQUIRE(((uintptr_t)workspace & 7) == 0, "workspace must be 8-byte aligned");
-  G2GTiling t = g2g_tiling(n_bins);
   WeightsParams p;
   p.tau = tau; p.points = points; p.denom = denom; p.wtab = wtab; p.sum_w = sum_w;
   p.n_cells = n_cells; p.n_pad = g2g_round_up(n_cells, G2G_CELL_TILE);
-  p.n_bins = n_bins; p.n_groups = t.n_groups; p.bins_per_group = t.bins_per_group; p.bins_even = t.bins_even;
-  p.row_floats = t.row_floats;
+  p.n_bins = n_bins;
+  p.mma_table = reinterpret_cast<unsigned char*>(mma_table);
+  if (mma_table) {
+    G2G_REQUIRE(((uintptr_t)mma_table & 127) == 0, "table must be 128-byte aligned");
+    G2GMmaTiling t = g2g_mma_tiling(n_bins);
+    p.n_groups = t.n_groups; p.bins_per_group = t.bins_per_group; p.n_cols = t.n_cols;
+    p.bins_even = 0; p.row_floats = 0;
+  } else {
+    G2GTiling t = g2g_tiling(n_bins);
+    p.n_groups = t.n_groups; p.bins_per_group = t.bins_per_group; p.bins_even = t.bins_even;
+    p.row_floats = t.row_floats; p.n_cols = 0;
+  }
   int64_t blocks = g2g_ceil_div(p.n_pad, kWCells);
   p.counter = reinterpret_cast<unsigned int*>(workspace);
   p.partial = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) + 16);
   cudaStream_t st = (cudaStream_t)stream;
   G2G_CUDA_TRY(cudaMemsetAsync(p.counter, 0, 16, st));
   const size_t smem = (size_t)n_bins * (kWCells + 1 + 4) * sizeof(double);
-  if (smem > 48 * 1024)
-    G2G_CUDA_TRY(cudaFuncSetAttribute(weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  weights_kernel<<<(unsigned)blocks, kWThreads, smem, st>>>(p);
+  if (mma_table) {
+    if (smem > 48 * 1024)
+      G2G_CUDA_TRY(cudaFuncSetAttribute(weights_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weights_kernel<true><<<(unsigned)blocks, kWThreads, smem, st>>>(p);
+  } else {
+    if (smem > 48 * 1024)
+      G2G_CUDA_TRY(cudaFuncSetAttribute(weights_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    weights_kernel<false><<<(unsigned)blocks, kWThreads, smem, st>>>(p);
+  }
   G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
+}  // namespace
+
+extern "C" int g2g_weights(const double* tau, int64_t n_cells, const double* points, const double* denom,
+                           int32_t n_bins, float* wtab, double* sum_w, void* workspace,
+                           size_t workspace_bytes, void* stream) {
+  G2G_REQUIRE(wtab, "null pointer");
+  return launch_weights(tau, n_cells, points, denom, n_bins, wtab, nullptr, sum_w, workspace, workspace_bytes, stream);
+}
+
+extern "C" int g2g_weights_mma(const double* tau, int64_t n_cells, const double* points, const double* denom,
+                               int32_t n_bins, void* table, double* sum_w, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  G2G_REQUIRE(table, "null pointer");
+  return launch_weights(tau, n_cells, points, denom, n_bins, nullptr, table, sum_w, workspace, workspace_bytes, stream);
+}
+
+extern "C" int g2g_mma_layout(int64_t n_cells, int32_t n_bins, g2g_mma_layout_t* out) {
+  G2G_REQUIRE(out != nullptr, "null out");
+  G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
+  G2G_REQUIRE(n_cells >= 1, "n_cells must be positive");
+  G2GMmaTiling t = g2g_mma_tiling(n_bins);
+  out->n_groups = t.n_groups;
+  out->bins_per_group = t.bins_per_group;
+  out->n_cols = t.n_cols;
+  out->reserved = 0;
+  out->n_pad = g2g_round_up(n_cells, G2G_CELL_TILE);
+  // one work item = 128 genes x cells_per_item cells; a function of the cell count only (shard-invariant
+  // sums).  Items are whole 256-cell accumulation chains; about 24 per gene tile and side, at most 4096
+  // cells (the per-item f64 partial sums are then 5 % of the bytes streamed).
+  int64_t item = g2g_round_up(g2g_ceil_div(n_cells, 24), 256);
+  if (item < 1024) item = 1024;
+  if (item > 4096) item = 4096;
+  if (item > out->n_pad) item = out->n_pad;
+  out->cells_per_item = item;
+  out->n_split = g2g_ceil_div(out->n_pad, item);
+  out->table_bytes = (int64_t)t.n_groups * (out->n_pad / G2G_CELL_TILE) * (int64_t)g2g_mma_stage_bytes(t.n_cols);
   return G2G_OK;
 }
 

@@ -11,10 +11,15 @@ RECORD_KEYS = ("opt_cost", "trends", "musigma", "align_len", "flags", "nnz", "al
 
 
 def shard_range(n_genes, rank, world):
-    """Contiguous block [lo, hi) of genes owned by ``rank``: ceil(G / world) genes per rank."""
-    per = -(-n_genes // world)
-    lo = min(n_genes, rank * per)
-    return lo, min(n_genes, lo + per)
+    """Contiguous block [lo, hi) of genes owned by ``rank``.  Balanced split: block sizes differ by at
+    most one and no rank is left empty while another holds two genes (with fewer genes than ranks the
+    surplus ranks own an empty block, which every caller must accept)."""
+    return n_genes * rank // world, n_genes * (rank + 1) // world
+
+
+def max_shard(n_genes, world):
+    """Largest block ``shard_range`` hands out: the fixed record count every rank sends to the gather."""
+    return -(-n_genes // world) if n_genes else 0
 
 
 def pack_records(tensors):

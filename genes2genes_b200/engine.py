@@ -109,32 +109,52 @@ def upload_small(arrays, device):
 
 
 class DeviceSide:
-    """Device-resident state of one dataset: packed expression matrix, weight table, workspaces."""
+    """Device-resident state of one dataset: packed expression matrix, weight table, workspaces.
 
-    def __init__(self, X, tau_dev, n_genes, n_bins, denom_dev, device):
+    ``variant`` selects the interpolation kernel the buffers are laid out for: ``"ffma"`` (K1
+    ``g2g_moments``, f32 weight table), ``"mma"`` (K1m ``g2g_moments_mma``, f16 hi/lo B-operand table) or ``"csc"`` (K1s, sparse input)."""
+
+    def __init__(self, X, tau_dev, n_genes, n_bins, denom_dev, device, variant="ffma"):
         # X: dense f32 [n_cells, ld] (time-sorted rows, ld % 4 == 0) or a CscMatrix (gene-major sparse)
         self.csc = X if isinstance(X, CscMatrix) else None
         self.X = None if self.csc is not None else X
         self.n_cells = int(X.shape[0])
         self.ld = 0 if self.csc is not None else int(X.shape[1])
-        self.n_genes = n_genes
-        lay = _lib.layout(self.n_cells, n_bins)
-        self.layout = lay
+        self.n_genes, self.n_bins, self.device = n_genes, n_bins, device
         self.tau = tau_dev
         self.denom = denom_dev
-        self.wtab = torch.empty(lay.n_groups * lay.n_pad * lay.row_floats, dtype=torch.float32, device=device)
         self.sum_w = torch.empty(n_bins, dtype=torch.float64, device=device)
         ws = _lib.load().g2g_weights_workspace_bytes(self.n_cells, n_bins)
         self.ws = torch.empty((ws + 7) // 8, dtype=torch.float64, device=device)
         self.ws_bytes = ws
         self.pilot = torch.empty(n_genes, dtype=torch.float32, device=device)
         self.g_stride = n_genes
-        self.part_f64 = torch.empty(lay.n_split * (2 * n_bins + 1) * n_genes, dtype=torch.float64, device=device)
-        self.part_i32 = torch.empty(lay.n_split * n_bins * n_genes, dtype=torch.int32, device=device)
+        self.variant = None
+        self.configure(variant)
+
+    def configure(self, variant):
+        """(Re)allocate the weight table and the partial-sum planes for ``variant``."""
+        if variant == self.variant:
+            return
+        n_bins, n_genes, device = self.n_bins, self.n_genes, self.device
+        self.wtab = self.part_f64 = self.part_i32 = None   # release before allocating the new set
+        if variant == "mma":
+            lay = _lib.mma_layout(self.n_cells, n_bins)
+            self.wtab = torch.empty(int(lay.table_bytes), dtype=torch.uint8, device=device)
+        else:
+            lay = _lib.layout(self.n_cells, n_bins)
+            self.wtab = torch.empty(lay.n_groups * lay.n_pad * lay.row_floats, dtype=torch.float32, device=device)
+        self.layout = lay
+        self.n_split = int(lay.n_split)
+        self.part_f64 = torch.empty(self.n_split * (2 * n_bins + 1) * n_genes, dtype=torch.float64, device=device)
+        self.part_i32 = torch.empty(self.n_split * n_bins * n_genes, dtype=torch.int32, device=device)
+        self.variant = variant
 
     def c_side(self):
+        mma = self.variant == "mma"
         return Side(self.X.data_ptr() if self.X is not None else None, self.n_cells, self.ld, self.wtab.data_ptr(),
-                    self.pilot.data_ptr(), self.part_f64.data_ptr(), self.part_i32.data_ptr())
+                    self.pilot.data_ptr(), self.part_f64.data_ptr(), self.part_i32.data_ptr(),
+                    self.n_split if mma else 0)
 
     def c_sparse_side(self):
         c = self.csc
@@ -273,8 +293,14 @@ class AlignmentEngine:
     trends, cost + DP + traceback) and returns itself; the results are views of ``self.packed``.
     """
 
+    #: smallest number of interpolation points the tensor-core interpolation kernel is used for: below it
+    #: the FFMA2 register tile of g2g_moments is at the HBM / FP32 ridge already (DESIGN.md section 4)
+    MMA_MIN_BINS = 30
+
     def __init__(self, X_ref, tau_ref, X_query, tau_query, n_genes, n_bins, denom_ref, denom_query,
-                 free_params=(0.99, 0.1, 0.7), device=None):
+                 free_params=(0.99, 0.1, 0.7), device=None, moments="auto"):
+        """``moments``: ``"auto"`` (tensor cores from ``MMA_MIN_BINS`` interpolation points, else the FFMA2
+        kernel), ``"mma"`` or ``"ffma"``."""
         self.lib = _lib.load()
         _lib.check(self.lib.g2g_check_device(), "g2g_check_device")
         self.device = device if device is not None else X_ref.device
@@ -291,8 +317,17 @@ class AlignmentEngine:
             "denom_ref": np.asarray(denom_ref, dtype=np.float64),
             "denom_query": np.asarray(denom_query, dtype=np.float64), "points": self.points_host,
             "eps_mean": self.eps.mean(axis=1), "eps_std": self.eps.std(axis=1)}, dev)
-        self.ref = DeviceSide(X_ref, small["tau_ref"], G, T, small["denom_ref"], dev)
-        self.query = DeviceSide(X_query, small["tau_query"], G, T, small["denom_query"], dev)
+        if moments not in ("auto", "mma", "ffma"):
+            raise ValueError("moments must be 'auto', 'mma' or 'ffma'")
+        if self.sparse:
+            self.variant = "csc"
+        elif moments == "mma" or (moments == "auto" and T >= self.MMA_MIN_BINS):
+            self.variant = "mma"
+        else:
+            self.variant = "ffma"
+        self.ref = DeviceSide(X_ref, small["tau_ref"], G, T, small["denom_ref"], dev, self.variant)
+        self.query = DeviceSide(X_query, small["tau_query"], G, T, small["denom_query"], dev, self.variant)
+        self.k1_status = torch.zeros(2, dtype=torch.int32, device=dev)
         self.points, self.eps_mean, self.eps_std = small["points"], small["eps_mean"], small["eps_std"]
         self.set_state_params(free_params)
         self.start = start_costs()
@@ -310,9 +345,7 @@ class AlignmentEngine:
         for k, n in zip(self.RESULT_KEYS, sizes):
             setattr(self, k, self.packed[off:off + n].view(shapes[k][1]).reshape(shapes[k][0]))
             off += n
-        self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
-        self._sparse_sides = (SparseSide * 2)(self.ref.c_sparse_side(), self.query.c_sparse_side()) \
-            if self.sparse else None
+        self._bind_sides()
         self.fix_ws_bytes = self.lib.g2g_fixup_workspace_bytes(G, T)
         self.fix_ws = torch.empty((self.fix_ws_bytes + 7) // 8, **f64)
         self.launches_per_run = 0
@@ -322,6 +355,20 @@ class AlignmentEngine:
         self._ev_fork = torch.cuda.Event()
         self._ev_join = torch.cuda.Event()
         self._ev_join2 = torch.cuda.Event()
+
+    def _bind_sides(self):
+        self._sides = (Side * 2)(self.ref.c_side(), self.query.c_side())
+        self._sparse_sides = (SparseSide * 2)(self.ref.c_sparse_side(), self.query.c_sparse_side()) \
+            if self.sparse else None
+
+    def use_variant(self, variant):
+        """Switch the dense interpolation kernel (``"mma"`` / ``"ffma"``); buffers are re-laid out."""
+        if self.sparse or variant == self.variant:
+            return
+        self.variant = variant
+        self.ref.configure(variant)
+        self.query.configure(variant)
+        self._bind_sides()
 
     def set_state_params(self, free_params):
         self.free_params = tuple(float(v) for v in free_params)
@@ -339,8 +386,9 @@ class AlignmentEngine:
         for s, stream in ((self.query, self._side_stream), (self.ref, self._side_stream2)):
             stream.wait_event(self._ev_fork)
             st = ctypes.c_void_p(stream.cuda_stream)
-            _lib.check(lib.g2g_weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
-                                       _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
+            weights = lib.g2g_weights_mma if self.variant == "mma" else lib.g2g_weights
+            _lib.check(weights(_ptr(s.tau), s.n_cells, _ptr(self.points), _ptr(s.denom), T, _ptr(s.wtab),
+                               _ptr(s.sum_w), _ptr(s.ws), s.ws_bytes, st), "g2g_weights")
         if not self.sparse:
             st = _stream()
             for s in (self.ref, self.query):
@@ -350,10 +398,7 @@ class AlignmentEngine:
         cur.wait_event(self._ev_join)
         cur.wait_event(self._ev_join2)
         st = _stream()
-        if self.sparse:
-            _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
-        else:
-            _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+        self._launch_moments(st)
         if with_dp:
             trans_c = (c_f64 * 25)(*np.asarray(self.trans, dtype=np.float64).reshape(-1).tolist())
             start_c = (c_f64 * 3)(*np.asarray(self.start, dtype=np.float64).tolist())
@@ -383,16 +428,20 @@ class AlignmentEngine:
         return run_cost_dp(trends, self.n_bins, self.trans, self.start, self.c_model, cost_in=cost_in, dump=dump,
                            out=out)
 
+    def _launch_moments(self, st):
+        lib, T, G = self.lib, self.n_bins, self.n_genes
+        if self.variant == "csc":
+            _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
+        elif self.variant == "mma":
+            _lib.check(lib.g2g_moments_mma(self._sides, 2, G, G, T, _ptr(self.k1_status), st), "g2g_moments_mma")
+        else:
+            _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+
     def time_moments(self, start_event, end_event):
         """Launch K1 alone between two CUDA events on the current stream (roofline measurement;
         the weight tables and pilot values of the last run are reused)."""
         start_event.record()
-        if self.sparse:
-            _lib.check(self.lib.g2g_moments_csc(self._sparse_sides, 2, self.n_genes, self.n_genes, self.n_bins,
-                                                _stream()), "g2g_moments_csc")
-        else:
-            _lib.check(self.lib.g2g_moments(self._sides, 2, self.n_genes, self.n_genes, self.n_bins, _stream()),
-                       "g2g_moments")
+        self._launch_moments(_stream())
         end_event.record()
 
     def run(self, fused=True):
@@ -417,17 +466,34 @@ class AlignmentEngine:
 
     def begin_results_to_host(self):
         """Enqueue the packed device->host copy on the current stream and return at once."""
-        if self._host_buf is None or self._host_buf.numel() != self.packed.numel():
-            self._host_buf = _pinned_buffer(self.packed.numel())
+        self._host_buf = _take_pinned(self.packed.numel())   # private until finish_results_to_host returns it
         self._host_buf.copy_(self.packed, non_blocking=True)
+        if self.variant == "mma":
+            self._status_host = _take_pinned(8)
+            self._status_host.copy_(self.k1_status.view(torch.uint8), non_blocking=True)
         self._pending_parts = [getattr(self, k) for k in self.RESULT_KEYS]
 
     def finish_results_to_host(self):
         """Wait for the copy started by ``begin_results_to_host``; returns name -> numpy array (views of
-        one private host copy of the staging buffer, which is reused by later calls)."""
+        one private host copy of the staging buffer, which goes back to the pool)."""
         torch.cuda.current_stream().synchronize()
+        if self.variant == "mma":
+            status = int(self._status_host.numpy().view(np.int32)[0])
+            _give_pinned(self._status_host)
+            self._status_host = None
+            if status & 1:
+                # a value did not fit the f16 split of the tensor-core kernel (|x - pilot| >= 255) or the input
+                # is not finite: redo the batch with the f32 kernel, which has no range limit
+                _give_pinned(self._host_buf)
+                self.k1_status.zero_()
+                self.use_variant("ffma")
+                self.run_interpolation(with_dp=True)
+                self.begin_results_to_host()
+                return self.finish_results_to_host()
         parts, self._pending_parts = self._pending_parts, None
         raw = self._host_buf.numpy().copy()
+        _give_pinned(self._host_buf)
+        self._host_buf = None
         host, off = {}, 0
         for k, t in zip(self.RESULT_KEYS, parts):
             n = t.numel() * t.element_size()
@@ -436,7 +502,21 @@ class AlignmentEngine:
         return host
 
 
-_PINNED = {}      # n_bytes -> [pinned buffer, event of the last copy that read or wrote it]
+_PINNED = {}      # n_bytes -> [pinned buffer, event of the last copy that read or wrote it]  (upload staging)
+_PINNED_FREE = {}  # n_bytes -> list of idle pinned result buffers
+
+
+def _take_pinned(n_bytes):
+    """A pinned host buffer nobody else holds (result copies): taken from / returned to a free list, so
+    two live engines or interleaved begin / finish calls never share one."""
+    free = _PINNED_FREE.setdefault(int(n_bytes), [])
+    return free.pop() if free else torch.empty(int(n_bytes), dtype=torch.uint8, pin_memory=True)
+
+
+def _give_pinned(buf):
+    free = _PINNED_FREE.setdefault(int(buf.numel()), [])
+    if len(free) < 4:
+        free.append(buf)
 
 
 def _pinned_buffer(n_bytes):

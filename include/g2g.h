@@ -84,6 +84,24 @@ int g2g_pack_csr(const int64_t* indptr, const int32_t* indices, const float* dat
                  void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * g2g_upload_block / g2g_scatter_rows -- the host->device leg of the same step, for a HOST matrix
+ * (`adata.X`, row major f32, cells x all genes), pipelined by row chunk: only the column block
+ * [col0, col0+n_cols) a rank needs crosses PCIe (one strided DMA per chunk, cudaMemcpy2DAsync; the
+ * source should be pinned), and every uploaded chunk is scattered to its time-sorted position while the
+ * next chunk is in flight.  Replaces `adata[:, gene_list]` + the pseudotime sort (Main.py:226-227,
+ * TimeSeriesPreprocessor.py:20) without a whole-matrix device copy.
+ *   g2g_upload_block: dst[r][c] = host_src[row0 + r][col0 + c], r < n_rows, c < n_cols (dst is a DEVICE
+ *     pointer, host_src the only HOST data pointer of the ABI).
+ *   g2g_scatter_rows: dst[dst_row[r]][g] = src[r][gene_idx[g]] (gene_idx null = identity), columns
+ *     n_genes..ld_dst-1 zero filled; dst_row i64 [n_rows] on the device.
+ */
+int g2g_upload_block(const float* host_src, int64_t ld_src, int64_t row0, int64_t n_rows, int64_t col0,
+                     int64_t n_cols, float* dst, int64_t ld_dst, void* stream);
+int g2g_scatter_rows(const float* src, int64_t n_rows, int64_t n_genes, int64_t ld_src,
+                     const int64_t* dst_row, const int32_t* gene_idx, float* dst, int64_t ld_dst,
+                     void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K0  g2g_weights -- Gaussian-kernel cell weights for one dataset.
  * Replaces TrajectoryInterpolator.compute_abs_timediff_mat / compute_Weight_matrix
  * (TimeSeriesPreprocessor.py:44-51, 122-133) and the window membership test of
@@ -132,14 +150,54 @@ typedef struct {
   const float* X;
   int64_t n_cells;
   int64_t ldx;
-  const float* wtab;
+  const float* wtab;             /* g2g_weights table (g2g_moments) or g2g_weights_mma table (g2g_moments_mma) */
   const float* pilot;
   double* part_f64;
   int32_t* part_i32;
+  int64_t n_split;               /* partial-sum planes in part_*: 0 = the count of g2g_layout() (g2g_moments);
+                                    g2g_moments_mma writes g2g_mma_layout().n_split planes: set it for K3 */
 } g2g_side_t;
 
 int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
                 int32_t n_bins, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1m g2g_moments_mma -- tensor-core variant of g2g_moments for 30 <= n_bins <= 128 (same reference code
+ * replaced: TSP.py:161-174, Main.py:298-301,344-363).  out[genes x bins] = X^T [genes x cells] . W [cells x bins]
+ * runs as tcgen05.mma kind::f16 (M = 128 genes = TMEM lanes, N = bins, K = 16 cells) with f32 accumulators
+ * in tensor memory.  To keep the f32 tolerance of the path: x and (x - a)^2 are split on the CUDA cores
+ * into f16 pairs (hi, lo * 2048) written to tensor memory as the A operand, the weights are split the same
+ * way by g2g_weights_mma into a shared-memory B operand table, and three products per moment are kept
+ * (hi.hi, lo.hi + hi.lo: 22 bits of each factor); sum (x - a) is added up on the CUDA cores.  The tensor core truncates when it accumulates
+ * (measured -1e-7 of the sum per 16-cell step, profiles/r02_umma_ts_probe.txt), so the hi.hi chains are
+ * cut every 256 cells: the accumulators are read back and added in f32 round-to-nearest registers, which
+ * are added in f64 once per work item.  Values with |x| >= 65504 or |x - a| >= 255 do not fit the f16
+ * split: the kernel then sets bit 0 of *status and the caller must redo the batch with g2g_moments.
+ *   sides[s].wtab = the table of g2g_weights_mma; part_f64 / part_i32 as for g2g_moments but with
+ *   g2g_mma_layout().n_split planes (set sides[s].n_split for K3); part_i32 is zeroed by the call
+ *   (counts are added with integer atomics).
+ *   status   i32 device word, OR-ed: bit 0 = non-finite accumulator (f16 range exceeded or non-finite input)
+ */
+typedef struct {
+  int32_t n_groups;              /* bin groups (X is streamed once per group): ceil(n_bins / 64) */
+  int32_t bins_per_group;
+  int32_t n_cols;                /* N of the MMA: bins_per_group rounded up to 16 */
+  int32_t reserved;
+  int64_t n_pad;                 /* n_cells rounded up to G2G_CELL_TILE */
+  int64_t cells_per_item;        /* depends on (n_cells, n_bins) only */
+  int64_t n_split;
+  int64_t table_bytes;           /* size of the g2g_weights_mma table for this dataset */
+} g2g_mma_layout_t;
+
+int g2g_mma_layout(int64_t n_cells, int32_t n_bins, g2g_mma_layout_t* out);
+/* g2g_weights for the tensor-core path: same arguments and the same sum_w (bit for bit); `table` receives,
+ * per bin group and per 64-cell stage, the f16 B operand of the stage's four K = 16 steps in the canonical
+ * K-major no-swizzle core-matrix layout (hi then lo * 2048 per step) followed by 64 window words. */
+int g2g_weights_mma(const double* tau, int64_t n_cells, const double* points, const double* denom,
+                    int32_t n_bins, void* table, double* sum_w, void* workspace, size_t workspace_bytes,
+                    void* stream);
+int g2g_moments_mma(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                    int32_t n_bins, int32_t* status, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1s g2g_moments_csc -- sparse variant of g2g_moments: the expression matrix
