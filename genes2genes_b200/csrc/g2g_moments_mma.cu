@@ -118,19 +118,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(smem_u32(bar)), "r"(parity)
       : "memory");
 }
-// wait of a role that is not latency critical (flushers): back off between probes so that the spin does
-// not take issue slots from the converters
+// wait of a role that is not latency critical (flushers): the probe may suspend the thread for up to a few
+// microseconds (suspend-time hint), so a waiting warp takes next to no issue slots from the converters
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
-  uint32_t done;
-  while (true) {
-    asm volatile(
-        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-        : "=r"(done)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-    if (done) break;
-    __nanosleep(256);
-  }
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP_R:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra WAIT_DONE_R;\n"
+      "bra WAIT_LOOP_R;\n"
+      "WAIT_DONE_R:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(4000u)
+      : "memory");
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
@@ -198,6 +198,30 @@ __device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
 }
 __device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
   return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+// packed f32x2 arithmetic (two cells of one gene per instruction)
+__device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
+  return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
+}
+__device__ __forceinline__ float lo_f(unsigned long long v) { return __uint_as_float((unsigned)(v & 0xffffffffull)); }
+__device__ __forceinline__ float hi_f(unsigned long long v) { return __uint_as_float((unsigned)(v >> 32)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// hi / lo f16 split of a packed pair: hi = f16(v), lo = f16((v - hi) * 2048)
+__device__ __forceinline__ void split2(unsigned long long v, uint32_t& hi, uint32_t& lo) {
+  hi = cvt_f16x2(lo_f(v), hi_f(v));
+  const float2 h = unpack_f16x2(hi);
+  // (v - h) is exact in f32; the negation rides on the f16 -> f32 conversion
+  const unsigned long long r = mul2(add2(v, pack2(-h.x, -h.y)), pack2(kLoScale, kLoScale));
+  lo = cvt_f16x2(lo_f(r), hi_f(r));
 }
 #ifdef __CUDA_FTZ
 #error "g2g_moments_mma.cu must be compiled without -ftz=true / --use_fast_math: nonzero_flag() relies on f32 denormals"
@@ -428,6 +452,7 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
       const MmaSide& s = p.side[it.side];
       const long long g = (long long)it.gt * kGT + gl;
       const float a = a_next;
+      const unsigned long long neg_a2 = pack2(-a, -a);
       if (item + (int)gridDim.x < p.n_items) {
         const Item nx = decode_item(p, item + gridDim.x);
         const long long gn = (long long)nx.gt * kGT + gl;
@@ -454,22 +479,20 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
           const float* xs = xt + (s4 * kStepCells) * kGT + gl;
           uint32_t xh[8], xl[8], yh[8], yl[8];
           int nz = 0;
-          float csum = 0.0f;
+          unsigned long long csum2 = 0ull;
           const long long step_row = it.row0 + (long long)tile * kStageCells + s4 * kStepCells;
           const bool all_valid = step_row + kStepCells <= n_cells;
 #pragma unroll
           for (int j = 0; j < ((G2G_MMA_ABLATE & 2) ? 1 : 8); ++j) {
             const float x0 = xs[(2 * j) * kGT], x1 = xs[(2 * j + 1) * kGT];
             nz += nonzero_flag(x0) + nonzero_flag(x1);
-            const float d0 = x0 - a, d1 = x1 - a;
-            const float y0 = d0 * d0, y1 = d1 * d1;
-            csum += d0 + d1;
-            xh[j] = cvt_f16x2(x0, x1);
-            yh[j] = cvt_f16x2(y0, y1);
-            const float2 xhf = unpack_f16x2(xh[j]), yhf = unpack_f16x2(yh[j]);
-            xl[j] = cvt_f16x2((x0 - xhf.x) * kLoScale, (x1 - xhf.y) * kLoScale);
-            yl[j] = cvt_f16x2((y0 - yhf.x) * kLoScale, (y1 - yhf.y) * kLoScale);
+            const unsigned long long x2 = pack2(x0, x1);
+            const unsigned long long d2 = add2(x2, neg_a2);
+            csum2 = add2(csum2, d2);
+            split2(x2, xh[j], xl[j]);
+            split2(mul2(d2, d2), yh[j], yl[j]);
           }
+          float csum = lo_f(csum2) + hi_f(csum2);
           if (!all_valid) {   // last step of a dataset: rows past n_cells are zero filled, leave them out
             csum = 0.0f;
             for (int c = 0; c < kStepCells; ++c)
