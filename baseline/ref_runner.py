@@ -1,10 +1,10 @@
-"""Import the UNMODIFIED reference (``/root/reference/genes2genes``) in the build
-container, behind stubs for the plotting / enrichment packages this image lacks.
+"""Import and run the UNMODIFIED reference package (Teichlab/Genes2Genes v0.2.0) behind stubs for the
+plotting / enrichment packages this image lacks (recipe: SURVEY.md section 8(c)).
 
-Test infrastructure only: used by ``make_golden.py`` to generate the committed
-fixtures.  Nothing under ``tests/`` marked ``gpu``, ``bench.py`` or
-``__graft_entry__`` imports this module (``/root/reference`` does not exist on
-the GPU box).  Recipe: SURVEY.md section 8(c).
+Where the package comes from: ``/root/reference`` in the build container, else ``baseline/_ref`` (the
+byte-for-byte copy ``baseline/install_reference.sh`` installs; it travels to the GPU box).  Used by
+``tests/golden/make_golden.py`` to generate the committed fixtures and by ``bench.py`` to time the
+reference's own CPU path (``cpu_baseline`` / ``--impl reference``).  The product never imports this module.
 """
 import importlib
 import os
@@ -14,7 +14,17 @@ import types
 import numpy as np
 import pandas as pd
 
-REFERENCE_ROOT = os.environ.get("G2G_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_reference():
+    for root in (os.environ.get("G2G_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")):
+        if root and os.path.isdir(os.path.join(root, "genes2genes")):
+            return root
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():
@@ -122,3 +132,26 @@ def import_reference():
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     return importlib.import_module("genes2genes")
+
+
+def time_reference(X_ref, time_ref, X_query, time_query, n_bins, concurrent=False, n_processes=None):
+    """Wall time of the reference's own ``RefQueryAligner(...)`` + ``align_all_pairs()`` on the given dense
+    arrays (cells x genes): (seconds, alignment strings).  ``concurrent=True`` uses the reference's
+    multiprocessing path (Main.py:438-448)."""
+    import contextlib
+    import io
+    import time
+    g2g = import_reference()
+    genes = ["g%d" % i for i in range(X_ref.shape[1])]
+    ar = make_adata(X_ref, time_ref, ["r%d" % i for i in range(X_ref.shape[0])], genes)
+    aq = make_adata(X_query, time_query, ["q%d" % i for i in range(X_query.shape[0])], genes)
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink), contextlib.redirect_stderr(sink):
+        t0 = time.perf_counter()
+        aligner = g2g.Main.RefQueryAligner(ar, aq, genes, int(n_bins))
+        if concurrent:
+            aligner.align_all_pairs(concurrent=True, n_processes=n_processes)
+        else:
+            aligner.align_all_pairs()
+        dt = time.perf_counter() - t0
+    return dt, [a.alignment_str for a in aligner.results]

@@ -1,21 +1,26 @@
 """bench.py -- gene alignments / second of the Genes2Genes hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--impl reference]
 
-One "step" = one pass of the hot path over one batch: interpolation of every gene of the workload
-(K0 weights, K1a pilot, K1 moments, K3 fix-up) + cost/DP/traceback (K4) (+ the NCCL gather of the
-per-gene result records to rank 0 when N > 1).  Workload at N=1: BASELINE.json configs[1]
-("C2": 1371 genes, 20,327 ref / 17,176 query cells, 14 interpolation points), synthetic data of that
-shape (genes2genes_b200/synthetic.py).  For N > 1 every rank aligns its own C2-sized gene shard
-(weak scaling; genes are independent).
+Workload (every N, strong scaling): BASELINE.json configs[3] "C4" -- 20,000 genes x (100,000 reference +
+100,000 query cells), 50 interpolation points, the shape the north-star target is quoted on; it fits one
+B200 (16 GB of f32 expression values).  Genes are sharded over the N ranks in contiguous blocks
+(genes2genes_b200/distributed.py); every rank generates ITS block of the synthetic matrices on its GPU
+(genes2genes_b200/synthetic.py: a gene's values do not depend on the sharding).
 
-Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM);
-`e2e` is the same metric through the public API (`Main.RefQueryAligner(...)` + `align_all_pairs()`)
-from pinned host buffers, with the host->device copies and the device->host result read inside
-the timed region.  `--impl reference` times the CPU port of the reference algorithm
-(oracle/g2g_oracle.py, per-gene loop like Main.py:449-455) on all host cores instead.
+One "step" = one pass of the hot path over the whole workload: K0 weight tables, K1a pilot means, K1m
+tensor-core interpolation, fused K3 + K4 (fix-up, cost, DP, traceback) on every rank's block, then the NCCL
+gather of the packed per-gene result records to rank 0 (overlapped with the next step's kernels).
+
+Prints ONE JSON line (rank 0).  `value` is device-resident throughput (inputs already in HBM); `e2e` is the
+same metric through the public API -- `Main.RefQueryAligner(adata_ref, adata_query, gene_list, 50,
+distributed=True)` + `align_all_pairs()` -- from pinned HOST matrices to host result objects on rank 0,
+with the host->device copies, the time sort, the gather and the device->host result read inside the timed
+region.  `--impl reference` times the reference package's own CPU path (baseline/_ref through
+baseline/ref_runner.py; the oracle port if the package is absent) on the box's host cores.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,41 +40,42 @@ UNIT = "genes/s"
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="C4")
     ap.add_argument("--dropout", type=float, default=0.9)
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--sparse", action="store_true", help="also report the sparse-input (CSC, work ~ nnz) variant")
-    ap.add_argument("--cpu-genes", type=int, default=512, help="genes in the bounded CPU-baseline sample")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the C2 / C3 sub-records (N = 1)")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--moments", default="auto", choices=["auto", "mma", "ffma"])
+    ap.add_argument("--cpu-genes-per-core", type=int, default=2, help="genes per host core in the bounded CPU sample")
     return ap.parse_args()
 
 
-def workload(name, dropout, rank=0):
+def shapes(name):
     from genes2genes_b200 import synthetic
-    G, nr, nq, T = synthetic.CONFIGS[name]
-    Xr, tr, Xq, tq, genes = synthetic.make_pair(G, nr, nq, dropout=dropout, seed=100 + rank)
-    return Xr, tr, Xq, tq, genes, T
+    return synthetic.CONFIGS[name]
 
 
 def config_dict(name, dropout, n_gpus, extra=None):
-    from genes2genes_b200 import synthetic
-    G, nr, nq, T = synthetic.CONFIGS[name]
+    G, nr, nq, T = shapes(name)
     cfg = {"workload": "%s: %d genes x (%d ref + %d query cells), %d interpolation points, dense f32 [cells x genes], "
-                       "synthetic log1p counts, dropout parameter %.2f (about 57%% zeros)" % (name, G, nr, nq, T, dropout),
-           "genes_per_gpu": G, "n_ref_cells": nr, "n_query_cells": nq, "n_interpolation_points": T,
-           "parallelism": "genes sharded over %d GPU(s), final NCCL gather to rank 0" % n_gpus if n_gpus > 1
-           else "single GPU", "l2": "L2 flushed (256 MiB write) between timed steps"}
+                       "synthetic log1p counts, dropout parameter %.2f" % (name, G, nr, nq, T, dropout),
+           "n_genes": G, "genes_per_gpu": -(-G // n_gpus), "n_ref_cells": nr, "n_query_cells": nq,
+           "n_interpolation_points": T,
+           "parallelism": ("genes sharded over %d GPUs in contiguous blocks, one NCCL gather of the result records "
+                           "to rank 0 per step" % n_gpus) if n_gpus > 1 else "single GPU",
+           "l2": "inputs larger than L2 (%.1f GB of expression values per rank per step); no flush"
+                 % (4.0 * (nr + nq) * (-(-G // n_gpus)) / 1e9)}
     if extra:
         cfg.update(extra)
     return cfg
 
 
 # ---------------------------------------------------------------------------------------------------
-# CPU arm: the oracle port, one gene at a time like the reference's loop (Main.py:449-455)
+# CPU arms
 # ---------------------------------------------------------------------------------------------------
 _CPU = {}
 
@@ -89,7 +95,6 @@ def _cpu_gene(g):
 
 
 def _one_blas_thread():
-    """Worker initialiser: one BLAS/OpenMP thread per process (the pool provides the parallelism)."""
     try:
         from threadpoolctl import threadpool_limits
         _CPU["_limit"] = threadpool_limits(1)
@@ -97,49 +102,116 @@ def _one_blas_thread():
         pass
 
 
-def cpu_port_rate(Xr, tr, Xq, tq, T, n_genes, n_procs):
-    """genes/s of the oracle port on `n_genes` genes of the workload with `n_procs` processes."""
-    sel = np.arange(min(n_genes, Xr.shape[1]))
-    Xr_s, Xq_s = np.ascontiguousarray(Xr[:, sel]), np.ascontiguousarray(Xq[:, sel])
+def cpu_port_rate(Xr, tr, Xq, tq, T, n_procs):
+    """genes/s of the oracle port (oracle/g2g_oracle.py, per-gene loop like Main.py:449-455)."""
+    n = Xr.shape[1]
+    import multiprocessing as mp
+    _cpu_init(Xr, Xq, tr, tq, T)
     if n_procs <= 1:
-        _cpu_init(Xr_s, Xq_s, tr, tq, T)
         _one_blas_thread()
         t0 = time.perf_counter()
-        for g in range(len(sel)):
+        for g in range(n):
             _cpu_gene(g)
-        return len(sel) / (time.perf_counter() - t0)
-    import multiprocessing as mp
+        return n / (time.perf_counter() - t0)
     ctx = mp.get_context("fork")
-    _cpu_init(Xr_s, Xq_s, tr, tq, T)  # inherited by the forked workers
     with ctx.Pool(n_procs, initializer=_one_blas_thread) as pool:
-        pool.map(_cpu_gene, range(min(n_procs, len(sel))))  # spin the workers up
+        pool.map(_cpu_gene, range(min(n_procs, n)))  # spin the workers up
         t0 = time.perf_counter()
-        pool.map(_cpu_gene, range(len(sel)), chunksize=max(1, len(sel) // (4 * n_procs)))
+        pool.map(_cpu_gene, range(n), chunksize=max(1, n // (4 * n_procs)))
         dt = time.perf_counter() - t0
-    return len(sel) / dt
+    return n / dt
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def cpu_sample(name, dropout, n_genes, device=None):
+    """`n_genes` genes of the workload at FULL cell counts as host arrays (evenly spaced gene indices)."""
+    from genes2genes_b200 import synthetic
+    G, nr, nq, T = shapes(name)
+    sel = np.unique(np.linspace(0, G - 1, min(G, n_genes)).astype(int))
+    if device is None:
+        Xr, tr, Xq, tq, _ = synthetic.make_pair(G, nr, nq, dropout=dropout, seed=100)
+        return Xr[:, sel].copy(), tr, Xq[:, sel].copy(), tq, T, sel
+    import torch
+    params = synthetic.gene_params(G, 100)
+    cols_r, cols_q = [], []
+    tr = tq = None
+    for g in sel:   # one 256-gene generator block per sampled gene: cheap on the GPU
+        xr, tr = synthetic.make_side_device(nr, params, 1, 0, device, int(g), int(g) + 1, dropout=dropout)
+        xq, tq = synthetic.make_side_device(nq, params, 2, 1, device, int(g), int(g) + 1, dropout=dropout, shift=0.08)
+        cols_r.append(xr[:, 0].cpu().numpy())
+        cols_q.append(xq[:, 0].cpu().numpy())
+    torch.cuda.synchronize()
+    return np.stack(cols_r, axis=1), tr, np.stack(cols_q, axis=1), tq, T, sel
+
+
+def cpu_reference_measure(name, dropout, genes_per_core, device=None):
+    """The CPU baseline of a record: the reference package's own RefQueryAligner + align_all_pairs on a bounded
+    gene sample of the workload at full cell counts -- sequential (1 core) and concurrent=True with one
+    process per core (Main.py:438-457) -- or, when the package is not present, the oracle port run the same
+    two ways.  Returns the cpu_baseline object (value = the all-cores rate)."""
+    from baseline import ref_runner
+    cores = os.cpu_count() or 1
+    n_conc = max(8, genes_per_core * cores)
+    n_seq = max(4, min(8, n_conc))
+    t0 = time.perf_counter()
+    Xr, tr, Xq, tq, T, sel = cpu_sample(name, dropout, n_conc, device)
+    out = {"unit": UNIT, "cores": cores, "cpu_model": cpu_model()}
+    if ref_runner.reference_available():
+        dt_seq, _ = ref_runner.time_reference(Xr[:, :n_seq], tr, Xq[:, :n_seq], tq, T)
+        dt_conc, _ = ref_runner.time_reference(Xr, tr, Xq, tq, T, concurrent=True, n_processes=cores)
+        out.update(kind="reference", value=len(sel) / dt_conc, sequential_value=n_seq / dt_seq,
+                   what="unmodified genes2genes v0.2.0 (baseline/_ref) RefQueryAligner + align_all_pairs, "
+                        "constructor included; value = concurrent=True with %d processes, sequential_value = 1 core"
+                        % cores)
+    else:
+        seq = cpu_port_rate(Xr[:, :n_seq], tr, Xq[:, :n_seq], tq, T, 1)
+        conc = cpu_port_rate(Xr, tr, Xq, tq, T, cores)
+        out.update(kind="port", value=conc, sequential_value=seq,
+                   what="oracle port (oracle/g2g_oracle.py align_gene_faithful): the reference package is not present")
+    out["sample"] = ("%d genes (concurrent) / %d genes (sequential) of the workload at full cell counts, %.0f s"
+                     % (len(sel), n_seq, time.perf_counter() - t0))
+    return out
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    Xr, tr, Xq, tq, genes, T = workload(args.workload, args.dropout)
-    cores = os.cpu_count() or 1
-    n_genes = min(Xr.shape[1], max(args.cpu_genes, 64 * cores))
-    rates = []
-    for _ in range(max(1, args.warmup > 0)):
-        cpu_port_rate(Xr, tr, Xq, tq, T, min(n_genes, 2 * cores), cores)
+    device = None
+    try:
+        import torch
+        if torch.cuda.is_available():
+            device = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    except Exception:
+        device = None
+    G, nr, nq, T = shapes(args.workload)
+    if device is None and G * (nr + nq) > 2e9:
+        emit({"impl": "reference", "unavailable": "no GPU to generate the %s sample and the host generator needs "
+              "%.0f GB" % (args.workload, 4e-9 * G * (nr + nq))})
+        return
+    rates, base = [], None
     t0 = time.perf_counter()
-    for _ in range(max(1, min(args.steps, 3))):
-        rates.append(cpu_port_rate(Xr, tr, Xq, tq, T, n_genes, cores))
+    n_steps = max(1, min(args.steps, 2))   # every step is a bounded sample; the run stays within minutes
+    for _ in range(n_steps):
+        base = cpu_reference_measure(args.workload, args.dropout, args.cpu_genes_per_core, device)
+        rates.append(base["value"])
     wall = time.perf_counter() - t0
     rate = float(np.mean(rates))
-    sample = "%d genes of the workload at full cell counts per step, %d worker processes (fork)" % (n_genes, cores)
+    base["value"] = rate
     line = {"impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
-            "steps": len(rates), "warmup": 1, "ms_per_step": 1e3 * wall / len(rates), "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps": n_steps, "warmup": 0, "ms_per_step": 1e3 * wall / n_steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args.workload, args.dropout, args.gpus),
-            "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": base,
             "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -194,83 +266,107 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload_name):
-    """DRAM bytes per K1 launch from the committed ncu capture of this workload, if any."""
+def ncu_traffic(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture of this configuration."""
     path = os.path.join(ROOT, "profiles", "k1_dram_traffic.json")
     try:
-        d = json.load(open(path))
-        return d.get(workload_name, {}).get("dram_bytes_per_launch")
+        return json.load(open(path)).get(key, {}).get("dram_bytes_per_launch")
     except Exception:
         return None
 
 
-def sparse_variant(args, Xr, tr, Xq, tq, genes, T, dev, flush_buf):
-    """The same workload handed over as scipy CSR (what real single-cell matrices are): the matrix stays
-    sparse on the device (K1s, work and PCIe bytes ~ stored entries).  Reported alongside the dense
-    numbers, at the generator's own density and thinned to a typical single-cell density."""
-    import scipy.sparse as sp
-    import torch
-    from genes2genes_b200 import Main, engine
-    from genes2genes_b200.anndata_lite import AnnDataLite
-    from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
-    out = []
-    rng = np.random.default_rng(0)
-    for keep in (1.0, 0.25):
-        Ar = Xr if keep == 1.0 else Xr * (rng.uniform(size=Xr.shape) < keep)
-        Aq = Xq if keep == 1.0 else Xq * (rng.uniform(size=Xq.shape) < keep)
-        cr, cq = sp.csr_matrix(Ar), sp.csr_matrix(Aq)
-        density = (cr.nnz + cq.nnz) / float(Ar.size + Aq.size)
+def result_digest(host):
+    """sha256 over every gene's integer results and optimal cost (bitwise shard invariant)."""
+    h = hashlib.sha256()
+    for k in ("align_len", "align_str", "flags", "nnz", "opt_cost", "l_states"):
+        h.update(np.ascontiguousarray(host[k]).tobytes())
+    return h.hexdigest()[:24]
+
+
+class DeviceWorkload:
+    """One rank's gene block of a workload on its GPU: packed (time-sorted) matrices + the engine."""
+
+    def __init__(self, name, dropout, lo, hi, dev, moments="auto", capacity=None, keep_raw=False):
+        import torch
+        from genes2genes_b200 import engine, synthetic
+        from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
+        G, nr, nq, T = shapes(name)
+        self.T, self.lo, self.hi, self.n_ref, self.n_query = T, lo, hi, nr, nq
+        Xr, tr, Xq, tq, genes = synthetic.make_pair_device(G, nr, nq, dev, lo, hi, dropout=dropout, seed=100)
+        self.tr, self.tq, self.genes = tr, tq, genes
+        self.raw = (Xr, Xq) if keep_raw else None
         tir = TrajectoryInterpolator(tr, T, adaptive_kernel=False).run()
         tiq = TrajectoryInterpolator(tq, T, adaptive_kernel=False).run()
-        eng = engine.AlignmentEngine(engine.pack_csc(cr, tir.order, None, len(genes), dev), tir.cell_pseudotimes,
-                                     engine.pack_csc(cq, tiq.order, None, len(genes), dev), tiq.cell_pseudotimes,
-                                     len(genes), T, tir.kernel_denominators(), tiq.kernel_denominators(), device=dev)
-        for _ in range(3):
-            eng.run()
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True),
-               torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        for a, b, c, d in ev:
-            flush_buf.fill_(3)
-            a.record(); eng.run(); b.record()
-            flush_buf.fill_(4)
-            eng.time_moments(c, d)
+        Xrd = engine.pack_dense(Xr, tir.order, None, dev)
+        Xqd = engine.pack_dense(Xq, tiq.order, None, dev)
+        del Xr, Xq
+        self.engine = engine.AlignmentEngine(Xrd, tir.cell_pseudotimes, Xqd, tiq.cell_pseudotimes, hi - lo, T,
+                                             tir.kernel_denominators(), tiq.kernel_denominators(), device=dev,
+                                             moments=moments, capacity=capacity)
         torch.cuda.synchronize()
-        step_ms = float(np.mean([a.elapsed_time(b) for a, b, _, _ in ev]))
-        k1_ms = float(np.mean([c.elapsed_time(d) for _, _, c, d in ev]))
-        saved = Main.RefQueryAligner.sparse_density_threshold
-        Main.RefQueryAligner.sparse_density_threshold = 1.0
-        try:
-            ar, aq = AnnDataLite(cr, tr, genes), AnnDataLite(cq, tq, genes)
-            t_e2e = []
-            for k in range(4):
-                torch.cuda.synchronize()
-                t0 = time.perf_counter()
-                al = Main.RefQueryAligner(ar, aq, genes, T, verbose=False)
-                al.align_all_pairs()
-                n = sum(a.alignment_str.count("M") for a in al.results)
-                torch.cuda.synchronize()
-                if k:
-                    t_e2e.append(time.perf_counter() - t0)
-                del al
-        finally:
-            Main.RefQueryAligner.sparse_density_threshold = saved
-        nnz_bytes = int(cr.data.nbytes + cr.indices.nbytes + cr.indptr.nbytes + cq.data.nbytes + cq.indices.nbytes
-                        + cq.indptr.nbytes)
-        out.append({"density": density, "ms_per_step": step_ms, "value": len(genes) / (step_ms * 1e-3),
-                    "k1s_kernel_ms": k1_ms, "nnz_gather_GBps": (cr.nnz + cq.nnz) * 72 / (k1_ms * 1e-3) / 1e9,
-                    "e2e_ms": float(np.mean(t_e2e)) * 1e3, "e2e_value": len(genes) / float(np.mean(t_e2e)),
-                    "h2d_bytes_per_step": nnz_bytes, "input": "scipy CSR on the host (pageable)"})
-        del eng
-    return out
+
+
+def capture_graph(eng):
+    """The kernel launches of one pass as a CUDA graph (None when capture is not possible)."""
+    import torch
+    try:
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            eng.run()
+            side.synchronize()
+            with torch.cuda.graph(g, stream=side):
+                eng.run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        return g
+    except Exception as exc:  # capture is an optimisation; fall back to eager launches
+        print("CUDA graph capture failed (%s); running eagerly" % exc, file=sys.stderr)
+        torch.cuda.synchronize()
+        return None
+
+
+def time_small_workload(name, dropout, dev, steps, warmup):
+    """Secondary record (N = 1): device-resident step time and the dominant kernel of a small configuration,
+    L2 flushed between steps."""
+    import torch
+    G, nr, nq, T = shapes(name)
+    w = DeviceWorkload(name, dropout, 0, G, dev)
+    eng = w.engine
+    eng.run()
+    torch.cuda.synchronize()
+    graph = capture_graph(eng)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    run = graph.replay if graph is not None else eng.run
+    for _ in range(warmup):
+        flush.fill_(1)
+        run()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in ev:
+        flush.fill_(2)
+        a.record(); run(); b.record()
+    k1 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in k1:
+        flush.fill_(3)
+        eng.time_moments(a, b)
+    torch.cuda.synchronize()
+    ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1]))
+    peak, _ = measured_peak()
+    alg = 4.0 * (nr + nq) * G + 8.0 * (nr + nq)
+    return {"workload": config_dict(name, dropout, 1)["workload"], "ms_per_step": ms, "value": G / (ms * 1e-3),
+            "unit": UNIT, "steps": steps, "l2": "flushed (256 MiB write) between steps", "cuda_graph": graph is not None,
+            "kernel": "moments_mma_kernel" if eng.variant == "mma" else "moments_kernel", "kernel_ms": k1_ms,
+            "roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peak}
 
 
 def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from genes2genes_b200 import Main, engine
+    from genes2genes_b200 import Main, distributed, engine
     from genes2genes_b200.anndata_lite import AnnDataLite
-    from genes2genes_b200.TimeSeriesPreprocessor import TrajectoryInterpolator
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -279,63 +375,53 @@ def run_b200(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    Xr, tr, Xq, tq, genes, T = workload(args.workload, args.dropout, rank)
-    G = len(genes)
+    G, nr, nq, T = shapes(args.workload)
+    lo, hi = distributed.shard_range(G, rank, world)
+    cap = distributed.max_shard(G, world)
+    all_genes = ["g%d" % i for i in range(G)]
 
-    # ---- device-resident arm -----------------------------------------------------------------------
-    tir = TrajectoryInterpolator(tr, T, adaptive_kernel=False).run()
-    tiq = TrajectoryInterpolator(tq, T, adaptive_kernel=False).run()
-    Xrd = engine.pack_dense(Xr, tir.order, None, dev)
-    Xqd = engine.pack_dense(Xq, tiq.order, None, dev)
-    eng = engine.AlignmentEngine(Xrd, tir.cell_pseudotimes, Xqd, tiq.cell_pseudotimes, G, T,
-                                 tir.kernel_denominators(), tiq.kernel_denominators(), device=dev)
-    gather = None
-    if world > 1:
-        from genes2genes_b200 import distributed
-        gather = distributed.ResultGather(eng, dst=0)
-    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
-                 for _ in range(args.steps)]
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    def step():
-        eng.run()
-        if gather is not None:
-            gather.run()
-
-    step()  # first run sets kernel attributes / loads modules
+    # ---- device-resident arm ------------------------------------------------------------------------
+    w = DeviceWorkload(args.workload, args.dropout, lo, hi, dev, moments=args.moments, capacity=cap, keep_raw=True)
+    eng = w.engine
+    # pinned host copies of this rank's blocks in the ORIGINAL cell order: the e2e arm's inputs
+    Xr_pin = torch.empty(w.raw[0].shape, dtype=torch.float32, pin_memory=True)
+    Xq_pin = torch.empty(w.raw[1].shape, dtype=torch.float32, pin_memory=True)
+    Xr_pin.copy_(w.raw[0]); Xq_pin.copy_(w.raw[1])
     torch.cuda.synchronize()
-    graph = None
-    if not args.no_graph:
-        # the 6 kernel launches of a step replay as one CUDA graph; the NCCL gather (N > 1) stays an
-        # eager call after the replay (a captured collective hung process-group teardown on this stack)
-        try:
-            g = torch.cuda.CUDAGraph()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                eng.run()
-                side.synchronize()
-                with torch.cuda.graph(g, stream=side):
-                    eng.run()
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            graph = g
-        except Exception as exc:  # capture is an optimisation; fall back to eager launches
-            print("CUDA graph capture failed (%s); running eagerly" % exc, file=sys.stderr)
-            graph = None
-            torch.cuda.synchronize()
+    w.raw = None
+    torch.cuda.empty_cache()
 
-    def timed_step():
+    eng.run()   # first run sets kernel attributes / loads modules
+    torch.cuda.synchronize()
+    graph = None if args.no_graph else capture_graph(eng)
+    # gather of step k overlaps step k+1: the packed records are copied to a send buffer at the end of the
+    # step (device to device), the collective runs on a side stream and is joined one step later
+    send = torch.empty_like(eng.packed)
+    recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    recv_list = list(recv.unbind(0)) if recv is not None else None
+    comm_stream = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+    gather_done = torch.cuda.Event()
+    step_done = torch.cuda.Event()
+
+    def one_step():
         if graph is not None:
             graph.replay()
-            if gather is not None:
-                gather.run()
         else:
-            step()
+            eng.run()
+        if world > 1:
+            main_stream.wait_event(gather_done)          # the previous gather has read `send`
+            send.copy_(eng.packed)
+            step_done.record(main_stream)
+            comm_stream.wait_event(step_done)
+            with torch.cuda.stream(comm_stream):
+                dist.gather(send, recv_list, dst=0)
+                gather_done.record(comm_stream)
 
+    gather_done.record(main_stream)
     for _ in range(args.warmup):
-        flush_buf.fill_(1)
-        timed_step()
+        one_step()
+    main_stream.wait_event(gather_done)
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -343,50 +429,57 @@ def run_b200(args):
         time.sleep(0.3)
     if world > 1:
         dist.barrier()   # after rank 0 started its clock sampler, so all ranks enter the timed loop together
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     wall0 = time.perf_counter()
-    for k in range(args.steps):
-        flush_buf.fill_(k & 0xFF)      # evict X and the partial sums from L2 (not timed)
-        starts[k].record()
-        timed_step()
-        ends[k].record()
+    t_start.record()
+    for _ in range(args.steps):
+        one_step()
+    main_stream.wait_event(gather_done)   # the last gather belongs to the timed region
+    t_end.record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     wall = time.perf_counter() - wall0
-    ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = float(np.sum(ms))
-    # the dominant kernel (K1 g2g_moments) alone, CUDA events on its launch stream, L2 flushed
-    k1_ms = []
-    for k in range(args.steps):
-        flush_buf.fill_(k & 0xFF)
-        a, b = k1_events[k]
+    total_ms = t_start.elapsed_time(t_end)
+    # the dominant kernel alone (CUDA events on its launch stream; inputs >> L2)
+    k1_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in k1_events:
         eng.time_moments(a, b)
     torch.cuda.synchronize()
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
+    # the fused fix-up + DP launch alone
     clocks = sampler.finish() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * G / (ms_per_step * 1e-3)
+    value = G / (ms_per_step * 1e-3)
 
-    # ---- end-to-end arm: public API, pinned host inputs -> host results --------------------------------
-    Xr_pin = torch.from_numpy(Xr).pin_memory()
-    Xq_pin = torch.from_numpy(Xq).pin_memory()
+    # sharded == single-GPU: rank 0 recomputes the LAST rank's block on its own GPU and compares the records
+    shard_check = None
+    if world > 1 and rank == 0:
+        lo2, hi2 = distributed.shard_range(G, world - 1, world)
+        w2 = DeviceWorkload(args.workload, args.dropout, lo2, hi2, dev, moments=args.moments, capacity=cap)
+        w2.engine.run()
+        torch.cuda.synchronize()
+        shard_check = {"block": "rank %d's genes [%d, %d) recomputed on rank 0" % (world - 1, lo2, hi2),
+                       "records_identical": bool(torch.equal(w2.engine.packed, recv[world - 1]))}
+        del w2
+        torch.cuda.empty_cache()
+
+    # ---- end-to-end arm: public API, pinned host blocks -> host result objects on rank 0 ----------------
     e2e_ms, ctor_ms = [], []
-    d2h = 0
-    # the AnnData-like inputs exist before the timed call (their X lives in pinned host memory)
-    adata_ref, adata_query = AnnDataLite(Xr_pin, tr, genes), AnnDataLite(Xq_pin, tq, genes)
+    d2h, digest = 0, None
+    adata_ref = AnnDataLite(Xr_pin[:, :hi - lo] if Xr_pin.shape[1] != hi - lo else Xr_pin, w.tr, w.genes)
+    adata_query = AnnDataLite(Xq_pin[:, :hi - lo] if Xq_pin.shape[1] != hi - lo else Xq_pin, w.tq, w.genes)
     for k in range(args.e2e_steps + 1 if args.e2e_steps > 0 else 0):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        aligner = Main.RefQueryAligner(adata_ref, adata_query, genes, T, verbose=False)
+        aligner = Main.RefQueryAligner(adata_ref, adata_query, all_genes, T, verbose=False, distributed=world > 1)
         t_ctor = time.perf_counter() - t0     # returns with the uploads still in flight
         aligner.align_all_pairs()
         n_match = sum(a.alignment_str.count("M") for a in aligner.results)  # touch every result
@@ -396,58 +489,61 @@ def run_b200(args):
             e2e_ms.append(dt * 1e3)
             ctor_ms.append(t_ctor * 1e3)
         d2h = int(sum(v.nbytes for v in aligner._host.values() if hasattr(v, "nbytes")))
+        if rank == 0:
+            digest = result_digest(aligner._host)
+            n_results = len(aligner.results)
         del aligner
     e2e_t = float(np.mean(e2e_ms)) * 1e-3 if e2e_ms else float("nan")
     if world > 1:
         t = torch.tensor([e2e_t], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_t = float(t.item())
-    h2d = int(Xr.nbytes + Xq.nbytes + tr.nbytes + tq.nbytes)
-
-    sparse_report = None
-    if world == 1 and args.sparse:
-        sparse_report = sparse_variant(args, Xr, tr, Xq, tq, genes, T, dev, flush_buf)
+    h2d = int(4 * (nr + nq) * G + 8 * (nr + nq) * world)   # all ranks: column blocks + pseudotimes
 
     if rank == 0:
         peak, peak_src = measured_peak()
-        nr, nq = Xr.shape[0], Xq.shape[0]
-        alg_bytes = 4.0 * (nr + nq) * G + 8.0 * (nr + nq)
+        n_loc = hi - lo
+        alg_bytes = 4.0 * (nr + nq) * n_loc + 8.0 * (nr + nq)
         k1 = float(np.mean(k1_ms)) * 1e-3
         achieved = alg_bytes / k1 / 1e9
+        mma = eng.variant == "mma"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 products / f64 accumulation (interpolation), f64 (cost + DP)",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None,
+            "dtype": ("f16 hi/lo split operands, f32 tensor-core chains of 256 cells, f32/f64 accumulation (interpolation); "
+                      "f64 (cost + DP)") if mma else "f32 products / f64 accumulation (interpolation), f64 (cost + DP)",
             "data": "synthetic",
             "config": config_dict(args.workload, args.dropout, world,
-                                  {"cuda_graph": graph is not None, "wall_s_timed_region": wall}),
-            "e2e": {"value": world * G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  {"cuda_graph": graph is not None, "wall_s_timed_region": wall,
+                                   "gather": "overlapped with the next step on a side stream" if world > 1 else "none"}),
+            "e2e": {"value": G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t * 1e3, "steps": len(e2e_ms),
                     "ms_each": [round(v, 3) for v in e2e_ms],
                     "constructor_ms": round(float(np.mean(ctor_ms)), 3) if ctor_ms else None,
-                    "what": "Main.RefQueryAligner(...) + align_all_pairs() from pinned host arrays to host result objects"},
+                    "results_on_rank0": n_results if e2e_ms else None,
+                    "what": "Main.RefQueryAligner(..., distributed=%s) + align_all_pairs() from pinned host column "
+                            "blocks (original cell order) to host result objects on rank 0" % (world > 1)},
             "gpu_launches": eng.launches_per_run * args.steps,
-            "roofline": {"kernel": "moments_kernel (K1 g2g_moments)", "bound": "hbm", "achieved": achieved,
-                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(args.workload),
+            "roofline": {"kernel": "moments_mma_kernel (K1m g2g_moments_mma)" if mma else "moments_kernel (K1 g2g_moments)",
+                         "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": ncu_traffic("%s_n%d" % (args.workload, world)),
                          "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
-                         "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / (float(np.mean(ms))),
-                         # informational: the kernel is FP32-FMA bound before it is HBM bound
-                         "compute": {"flops_per_launch": 2.0 * (2 * T + 1) * (nr + nq) * G,
-                                     "achieved_tflops": 2.0 * (2 * T + 1) * (nr + nq) * G / k1 / 1e12,
-                                     "peak_tflops": 57.2, "frac": 2.0 * (2 * T + 1) * (nr + nq) * G / k1 / 1e12 / 57.2,
-                                     "peak_source": "FFMA2 issue-rate micro-benchmark on this pool's B200 "
-                                                    "(profiles/r01_fma_peak_microbench.txt; plain FFMA: 66.4)"}},
+                         "kernel_ms": k1 * 1e3, "kernel_share_of_step": k1 * 1e3 / ms_per_step,
+                         "genes_in_launch": n_loc,
+                         "tensor": {"flops_per_launch": 2.0 * 3 * 2 * 64 * (nr + nq) * n_loc,
+                                    "note": "six f16 MMAs (M 128, N 64, K 16) per 16 cells x 128 genes; the tensor "
+                                            "pipe is not the bound"} if mma else None},
+            "result_sha256_24": digest,
+            "shard_check": shard_check,
             "clocks": clocks,
         }
-        if sparse_report is not None:
-            line["sparse_variant"] = sparse_report
+        if world == 1 and not args.no_secondary:
+            del eng, w
+            torch.cuda.empty_cache()
+            line["secondary"] = [time_small_workload(n, args.dropout, dev, 20, 3) for n in ("C2", "C3")]
         if not args.no_cpu_baseline and world == 1:
-            t0 = time.perf_counter()
-            rate = cpu_port_rate(Xr, tr, Xq, tq, T, args.cpu_genes, 1)
-            line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
-                                    "sample": "%d genes of the workload at full cell counts, oracle port "
-                                              "(oracle/g2g_oracle.py align_gene_faithful), %.1f s"
-                                              % (min(args.cpu_genes, G), time.perf_counter() - t0)}
+            line["cpu_baseline"] = cpu_reference_measure(args.workload, args.dropout, args.cpu_genes_per_core, dev)
         emit(line)
     if world > 1:
         del graph

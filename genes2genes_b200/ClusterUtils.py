@@ -1,9 +1,10 @@
-"""The two ``ClusterUtils`` functions every notebook calls right after alignment (SURVEY.md 8(f) row
-f2): the aggregate (cell-level) alignment over a gene set and the pairwise match-count matrix.  The
-per-gene counting loops of the reference (ClusterUtils.py:435-450, 471-490) run as two small CUDA
-kernels (``csrc/g2g_aggregate.cu``) over the batch's result arrays; the walk over the (T+1) x (S+1)
-grid stays on the host.  The rest of the reference's ``ClusterUtils`` (clustering, Levenshtein
-distances) is out of scope.
+"""The ``ClusterUtils`` functions on or next to the alignment hot path:
+the aggregate (cell-level) alignment over a gene set and the pairwise match-count matrix, whose per-gene
+counting loops (ClusterUtils.py:435-450, 471-490) run as two small CUDA kernels
+(``csrc/g2g_aggregate.cu``) over the batch's result arrays while the walk over the (T+1) x (S+1) grid
+stays on the host; and the Levenshtein / Hamming distance matrices between alignment strings
+(ClusterUtils.py:21-38, 361-377; ``csrc/g2g_strdist.cu``).  The clustering itself (agglomerative
+clustering, plots) is out of scope.
 """
 import ctypes
 
@@ -36,14 +37,20 @@ def _device_counts(aligner, gene_set, which):
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         mask_d = torch.from_numpy(mask).to(dev)
         G = len(mask)
+        cache = store.__dict__.setdefault("_device_arrays", {})   # device copies of the result arrays, made once
+
+        def on_device(key):
+            if key not in cache:
+                cache[key] = torch.from_numpy(np.ascontiguousarray(host[key])).to(dev)
+            return cache[key]
         if which == "states":
-            src = torch.from_numpy(np.ascontiguousarray(host["l_states"])).to(dev)
+            src = on_device("l_states")
             out = torch.empty((5, T + 1, T + 1), dtype=torch.int32, device=dev)
             _lib.check(lib.g2g_state_histogram(src.data_ptr(), G, T, mask_d.data_ptr(), out.data_ptr(), st),
                        "g2g_state_histogram")
         else:
-            s = torch.from_numpy(np.ascontiguousarray(host["align_str"])).to(dev)
-            n = torch.from_numpy(np.ascontiguousarray(host["align_len"])).to(dev)
+            s = on_device("align_str")
+            n = on_device("align_len")
             out = torch.empty((T + 1, T + 1), dtype=torch.int32, device=dev)
             _lib.check(lib.g2g_match_counts(s.data_ptr(), n.data_ptr(), G, T, mask_d.data_ptr(), out.data_ptr(), st),
                        "g2g_match_counts")

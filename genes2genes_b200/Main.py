@@ -468,9 +468,11 @@ class RefQueryAligner:
         self.adata_ref_full, self.adata_query_full = adata_ref, adata_query
         self._all_genes = list(gene_list)
         self._shard = (0, len(gene_list))
+        self._capacity = None
         if self._dist is not None:
             from . import distributed as _distributed
             self._shard = _distributed.shard_range(len(gene_list), *self._dist)
+            self._capacity = _distributed.max_shard(len(gene_list), self._dist[1])
             gene_list = self._all_genes[self._shard[0]:self._shard[1]]
         self._local_genes = list(gene_list)
         self.gene_list = gene_list
@@ -481,10 +483,6 @@ class RefQueryAligner:
         self.state_params = [0.99, 0.1, 0.7]  # same defaults as the reference (Main.py:218)
         self.no_extreme_cases = False
 
-        # start the host->device copies of the expression matrices first: the pseudotime sort and the
-        # kernel-width computation below run on the host while the DMA engine streams them
-        with torch.cuda.device(self.device):
-            raw_ref, raw_query = self._upload(adata_ref), self._upload(adata_query)
         k = 1
         self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
             self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
@@ -497,21 +495,24 @@ class RefQueryAligner:
             self._both_sparse = _sp.issparse(adata_ref.X) and _sp.issparse(adata_query.X)
         except Exception:
             self._both_sparse = False
-        with torch.cuda.device(self.device):
-            Xr = self._pack(adata_ref, self.TrajInt_R.order, raw_ref)
-            Xq = self._pack(adata_query, self.TrajInt_Q.order, raw_query)
-            del raw_ref, raw_query
-            if isinstance(Xr, _engine.CscMatrix) != isinstance(Xq, _engine.CscMatrix):
-                # one side fell over the density threshold: densify the sparse one too
-                self._both_sparse = False
-                if isinstance(Xr, _engine.CscMatrix):
-                    Xr = self._pack(adata_ref, self.TrajInt_R.order)
-                else:
-                    Xq = self._pack(adata_query, self.TrajInt_Q.order)
-            self._engine = _engine.AlignmentEngine(
-                Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(self._local_genes),
-                self.n_artificial_time_points, self.TrajInt_R.kernel_denominators(),
-                self.TrajInt_Q.kernel_denominators(), self.state_params, self.device)
+        self._engine = None
+        if len(self._local_genes) > 0:   # a rank of a multi-GPU job may own no gene at all (fewer genes than ranks)
+            with torch.cuda.device(self.device):
+                # the host->device copies are asynchronous: the second dataset is packed, the weight tables and
+                # the engine's buffers are set up while the DMA engine streams the first
+                Xr = self._pack(adata_ref, self.TrajInt_R.order)
+                Xq = self._pack(adata_query, self.TrajInt_Q.order)
+                if isinstance(Xr, _engine.CscMatrix) != isinstance(Xq, _engine.CscMatrix):
+                    # one side fell over the density threshold: densify the sparse one too
+                    self._both_sparse = False
+                    if isinstance(Xr, _engine.CscMatrix):
+                        Xr = self._pack(adata_ref, self.TrajInt_R.order)
+                    else:
+                        Xq = self._pack(adata_query, self.TrajInt_Q.order)
+                self._engine = _engine.AlignmentEngine(
+                    Xr, self.TrajInt_R.cell_pseudotimes, Xq, self.TrajInt_Q.cell_pseudotimes, len(self._local_genes),
+                    self.n_artificial_time_points, self.TrajInt_R.kernel_denominators(),
+                    self.TrajInt_Q.kernel_denominators(), self.state_params, self.device, capacity=self._capacity)
         self._say("Interpolator initialization completed")
         self._interp = None
         self._say("Aligner initialised to align trajectories of", adata_ref.shape[0], "reference cells &",
@@ -522,36 +523,29 @@ class RefQueryAligner:
             print(*a)
 
     # -- input packing ------------------------------------------------------------------------------
-    def _upload(self, adata):
-        """Asynchronous device copy of a dense ``adata.X`` (None for sparse inputs, which are uploaded
-        in compressed form by ``_pack``)."""
-        import torch
-        X = adata.X
+    def _local_columns(self, adata):
+        """Where this aligner's (this rank's) genes sit in ``adata``: (col_lo, col_hi, idx) with ``idx`` the
+        positions relative to ``col_lo`` (None when the genes are exactly the contiguous block).  Only the
+        local genes need to be present in ``adata`` -- a rank of a multi-GPU job may load just its block."""
+        var_names = adata.var_names
+        local = self._local_genes
+        n_var = len(var_names)
+        if n_var == len(local) and all(str(a) == b for a, b in zip(var_names, local)):
+            return 0, n_var, None
+        pos = {str(g): k for k, g in enumerate(var_names)}
         try:
-            import scipy.sparse as sp
-            if sp.issparse(X):
-                return None
-        except Exception:
-            pass
-        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
-            X = X.todense()
-        if isinstance(X, np.matrix):
-            X = np.asarray(X)
-        if not torch.is_tensor(X):
-            X = torch.from_numpy(np.ascontiguousarray(X, dtype=np.float32))
-        if X.dtype != torch.float32:
-            X = X.to(torch.float32)
-        return X.to(self.device, non_blocking=True)
+            cols = np.asarray([pos[g] for g in local], dtype=np.int64)
+        except KeyError as exc:
+            raise KeyError("gene %s of gene_list is not in var_names" % exc) from None
+        lo, hi = int(cols.min()), int(cols.max()) + 1
+        if hi - lo == len(cols) and np.array_equal(cols, np.arange(lo, hi)):
+            return lo, hi, None
+        return lo, hi, (cols - lo).astype(np.int32)
 
-    def _pack(self, adata, order, raw=None):
-        """``adata[order][:, gene_list].X`` as a packed f32 device matrix (``raw``: the device copy of
-        a dense ``adata.X`` started by ``_upload``)."""
-        var_names = [str(v) for v in adata.var_names]
-        if list(self._local_genes) == var_names:
-            gene_idx = None
-        else:
-            pos = {g: k for k, g in enumerate(var_names)}
-            gene_idx = np.asarray([pos[g] for g in self._local_genes], dtype=np.int32)
+    def _pack(self, adata, order):
+        """``adata[order][:, gene_list].X`` as a packed f32 device matrix (or a ``CscMatrix``)."""
+        import torch
+        col_lo, col_hi, idx = self._local_columns(adata)
         X = adata.X
         identity = bool(np.all(order[1:] > order[:-1])) if len(order) > 1 else True
         row_order = None if identity else order
@@ -561,14 +555,25 @@ class RefQueryAligner:
         except Exception:  # scipy always ships with the reference's dependencies; be permissive
             is_sparse = False
         if is_sparse:
+            gene_idx = None
+            if not (col_lo == 0 and col_hi == X.shape[1] and idx is None):
+                gene_idx = (np.arange(col_lo, col_hi) if idx is None else col_lo + idx).astype(np.int32)
             X = X.tocsr()
+            if not X.has_canonical_format:   # duplicate (row, col) entries add up, like .todense()
+                X = X.copy()
+                X.sum_duplicates()
             density = X.nnz / max(1, X.shape[0] * X.shape[1])
             if self._both_sparse and density <= self.sparse_density_threshold:
                 return _engine.pack_csc(X, row_order, gene_idx, X.shape[1], self.device)
             return _engine.pack_csr(X, row_order, gene_idx, X.shape[1], self.device)
-        if raw is None:
-            raw = self._upload(adata)
-        return _engine.pack_dense(raw, row_order, gene_idx, self.device)
+        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
+            X = X.todense()
+        if isinstance(X, np.matrix):
+            X = np.asarray(X)
+        if torch.is_tensor(X) and X.device.type == "cuda":   # device-resident input: gather kernel
+            blk = X[:, col_lo:col_hi]
+            return _engine.pack_dense(blk, row_order, idx, self.device)
+        return _engine.upload_host_block(X, row_order, col_lo, col_hi, idx, self.device)
 
     @property
     def ref_mat(self):
@@ -608,12 +613,13 @@ class RefQueryAligner:
         import torch
         eng = self._engine
         with torch.cuda.device(self.device):
-            eng.set_state_params(self.state_params)
-            if self._interp is None:
-                eng.run_interpolation(with_dp=True)   # interpolation + fix-up + DP, fused launch
-                self._interp = True
-            else:
-                eng.run_dp()                          # new state_params: only the DP is repeated
+            if eng is not None:
+                eng.set_state_params(self.state_params)
+                if self._interp is None:
+                    eng.run_interpolation(with_dp=True)   # interpolation + fix-up + DP, fused launch
+                    self._interp = True
+                else:
+                    eng.run_dp()                          # new state_params: only the DP is repeated
             if self._dist is None:
                 eng.begin_results_to_host()
                 if on_enqueued is not None:
@@ -635,39 +641,52 @@ class RefQueryAligner:
         return host
 
     def _new_store(self, host):
-        return _ResultStore(host, self.gene_list, self.n_artificial_time_points, self._engine.eps,
+        return _ResultStore(host, self.gene_list, self.n_artificial_time_points,
+                            _engine.epsilon_table(self.n_artificial_time_points),
                             self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
                             self.state_params, self.device)
 
     def _gather_results(self):
-        """The one collective of the path: every rank's per-gene records go to rank 0 (NCCL gather)."""
+        """The one collective of the path: every rank's packed per-gene records go to rank 0 (NCCL gather of
+        equally sized byte buffers laid out for the largest shard).  Returns rank 0's host arrays for ALL
+        genes, the own block's on the other ranks."""
         import torch
         import torch.distributed as dist
         from . import distributed as D
         rank, world = self._dist
         eng, T = self._engine, self.n_artificial_time_points
         n_all = len(self._all_genes)
-        per = -(-n_all // world)
-        padded = {}
-        for k in D.RECORD_KEYS:
-            t = getattr(eng, k)
-            buf = torch.zeros((per,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-            buf[:t.shape[0]] = t
-            padded[k] = buf
-        send = D.pack_records(padded)
-        recv = [torch.empty_like(send) for _ in range(world)] if rank == 0 else None
-        dist.gather(send, recv, dst=0)
+        cap = self._capacity
+        n_bytes = D.record_bytes(cap, T)
+        if eng is not None:
+            send = eng.packed
+        else:   # empty shard: join the collective with an all-zero buffer
+            send = torch.zeros(max(n_bytes, 8), dtype=torch.uint8, device=self.device)
+        on_host = dist.get_backend() != "nccl"   # gloo (tests: several ranks on one GPU) gathers host buffers
+        if on_host:
+            torch.cuda.current_stream().synchronize()
+            send = send.cpu()
+        recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=send.device) if rank == 0 else None
+        dist.gather(send, list(recv.unbind(0)) if rank == 0 else None, dst=0)
         if rank != 0:
+            if eng is None:
+                return _engine.unpack_results(np.zeros(send.numel(), dtype=np.uint8), cap, T, 0)
             return eng.results_to_host()
-        tmpl = D.record_templates(per, T)
+        if on_host:
+            raw = recv.numpy()
+        else:
+            host_buf = _engine._take_pinned(recv.numel())
+            host_buf.copy_(recv.view(-1), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            raw = host_buf.numpy().reshape(world, -1).copy()
+            _engine._give_pinned(host_buf)
         parts = []
-        for r, b in enumerate(recv):
+        for r in range(world):
             lo, hi = D.shard_range(n_all, r, world)
-            rec = D.unpack_records(b, tmpl)
-            parts.append({k: v[:hi - lo].cpu().numpy() for k, v in rec.items()})
+            parts.append(_engine.unpack_results(raw[r], cap, T, hi - lo))
         self.gene_list = self._all_genes                    # rank 0 now holds every gene's result
         self._shard = (0, n_all)
-        return {k: np.concatenate([p[k] for p in parts]) for k in D.RECORD_KEYS}
+        return {k: np.concatenate([p[k] for p in parts]) for k in _engine.AlignmentEngine.RESULT_KEYS}
 
     def _make_result(self, idx, host=None):
         return AligmentObj(self._store, idx, self.gene_list[idx], host)
@@ -749,6 +768,46 @@ class RefQueryAligner:
         rows = [a.get_series_match_percentage() for a in self.results]
         df = pd.DataFrame(rows, columns=["match %", "match % S", "match % T"])
         df["cluster_id"] = getattr(self, "cluster_ids", [None] * len(rows))
+        return df
+
+    def get_stat_df(self, plot=True):
+        """Per-gene summary table of the reference (``get_stat_df``, Main.py:459-491): gene, alignment
+        similarity, optimal cost, log2 fold change of the mean expression, colour flag, sorted the same
+        way; prints the mean similarity.  The two plots are drawn when matplotlib / seaborn are installed
+        (``plot=False`` skips them)."""
+        import pandas as pd
+        ref_mat, query_mat = self.ref_mat, self.query_mat
+        rows = []
+        with np.errstate(all="ignore"):
+            for g in self.gene_list:
+                a = self.results_map[g]
+                rgex, qgex = np.asarray(ref_mat.loc[:, g]), np.asarray(query_mat.loc[:, g])
+                rows.append([g, a.match_percentage / 100, a.fwd_DP.opt_cost, np.log2(np.mean(rgex) / np.mean(qgex))])
+        df = pd.DataFrame(rows, columns=["Gene", "alignment_similarity_percentage", "opt_alignment_cost", "l2fc"])
+        df["color"] = np.repeat("green", df.shape[0])
+        df.loc[df["alignment_similarity_percentage"] <= 0.5, "color"] = "red"
+        df["abs_l2fc"] = np.abs(df["l2fc"])
+        df = df.sort_values(["alignment_similarity_percentage", "abs_l2fc"], ascending=[True, False])
+        print("Mean alignment similarity percentage (matched %): ")
+        print(round(np.mean(df["alignment_similarity_percentage"]), 4) * 100, "%")
+        if plot:
+            try:
+                import matplotlib.pyplot as plt
+                import seaborn as sb
+            except Exception:
+                return df
+            plt.subplots(1, 2, figsize=(10, 4))
+            plt.subplot(1, 2, 1)
+            sb.kdeplot(np.asarray([x * 100 for x in df["alignment_similarity_percentage"]]), fill=True,
+                       label="Alignment Similarity %")
+            plt.xlim([0, 100])
+            plt.xlabel("Alignment similarity percentage", fontsize="12")
+            plt.ylabel("Density", fontsize="12")
+            plt.subplot(1, 2, 2)
+            sb.scatterplot(x=df["alignment_similarity_percentage"] * 100, y=df["opt_alignment_cost"],
+                           hue=df["color"], palette={"green": "green", "red": "red"}, legend=False)
+            plt.xlabel("Alignment similarity percentage", fontsize="12")
+            plt.ylabel("Optimal alignment cost (nits)", fontsize="12")
         return df
 
     def get_stat_table(self):

@@ -18,9 +18,21 @@ class TrajectoryInterpolator:
     used to time-sort the cells (TimeSeriesPreprocessor.py:20).
     """
 
-    def __init__(self, time, n_bins, adaptive_kernel=True, kernel_WINDOW_SIZE=0.1, raising_degree=1,
+    def __init__(self, adata, n_bins, adaptive_kernel=True, kernel_WINDOW_SIZE=0.1, raising_degree=1,
                  gene_list=None, obs_names=None):
-        time = np.asarray(time, dtype=np.float64)
+        """``adata``: an AnnData-like object, as in the reference (``TrajectoryInterpolator(adata, n_bins,
+        ...)``, TimeSeriesPreprocessor.py:18), or just the pseudotime array of the cells (what the device path
+        needs; ``gene_list`` / ``obs_names`` then come from the keyword arguments)."""
+        self._adata = None
+        if hasattr(adata, "obs"):
+            self._adata = adata
+            time = np.asarray(adata.obs["time"], dtype=np.float64)
+            if obs_names is None:
+                obs_names = getattr(adata, "obs_names", None)
+            if gene_list is None:
+                gene_list = getattr(adata, "var_names", None)
+        else:
+            time = np.asarray(adata, dtype=np.float64)
         self.n_bins = int(n_bins)
         self.order = np.argsort(time)
         self.cell_pseudotimes = time[self.order]
@@ -29,8 +41,30 @@ class TrajectoryInterpolator:
         self.adaptive_kernel = adaptive_kernel
         self.k = raising_degree
         self.gene_list = gene_list
-        self.obs_names = obs_names
+        # cells are kept in pseudotime order (TimeSeriesPreprocessor.py:20): so are their names
+        self.obs_names = None if obs_names is None else np.asarray(obs_names)[self.order]
         self._weights = None
+        self._mat = None
+
+    @property
+    def adata(self):
+        """The time-sorted AnnData (TimeSeriesPreprocessor.py:20); only when built from one."""
+        if self._adata is None:
+            raise AttributeError("this TrajectoryInterpolator was built from a pseudotime array, not an AnnData")
+        return self._adata[self.order]
+
+    @property
+    def mat(self):
+        """genes x cells CSR matrix of the time-sorted cells (TimeSeriesPreprocessor.py:28), built on first
+        access; the device path streams the packed matrix instead."""
+        if self._mat is None:
+            from scipy.sparse import csr_matrix
+            X = self.adata.X
+            X = X.todense() if hasattr(X, "todense") else X
+            if hasattr(X, "cpu"):
+                X = X.cpu().numpy()
+            self._mat = csr_matrix(np.asarray(X).transpose())
+        return self._mat
 
     def run(self):
         if self.adaptive_kernel:

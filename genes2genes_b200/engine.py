@@ -208,6 +208,103 @@ def pack_dense(X, row_order, gene_idx, device):
     return out
 
 
+def _host_matrix_pointer(X):
+    """(address, leading dimension in floats, keep-alive object) of a row-major f32 host matrix, or None
+    when ``X`` is not one (other dtype / layout / device)."""
+    if torch.is_tensor(X):
+        if X.device.type == "cpu" and X.dtype == torch.float32 and X.dim() == 2 and (X.shape[1] == 1 or X.stride(1) == 1) \
+                and X.stride(0) >= X.shape[1]:
+            return X.data_ptr(), int(X.stride(0)), X
+        return None
+    if isinstance(X, np.ndarray) and not isinstance(X, np.matrix) and X.dtype == np.float32 and X.ndim == 2 \
+            and (X.shape[1] == 1 or X.strides[1] == 4) and X.strides[0] % 4 == 0 and X.strides[0] >= 4 * X.shape[1]:
+        return X.ctypes.data, X.strides[0] // 4, X
+    return None
+
+
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    key = torch.device(device).index
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
+def upload_host_block(X, row_order, col_lo, col_hi, gene_idx_rel, device, chunk_bytes=96 << 20):
+    """Packed device copy of ``X[row_order][:, col_lo:col_hi][:, gene_idx_rel]`` for a HOST matrix ``X``
+    (row-major f32, cells x all genes; ideally pinned): only the column block crosses PCIe, as strided
+    DMA copies of ``chunk_bytes`` (``g2g_upload_block``) on a copy stream, and every chunk is scattered to
+    its time-sorted rows (``g2g_scatter_rows``) while the next one is in flight.  No whole-matrix device
+    copy exists at any time: one [cells x ld] result plus two staging chunks.  ``row_order`` /
+    ``gene_idx_rel`` may be None (identity); with both None the block is copied straight into place."""
+    lib = _lib.load()
+    host = _host_matrix_pointer(X)
+    if host is None:   # other dtypes / layouts: make a f32 host copy of the column block only
+        blk = X[:, col_lo:col_hi]
+        blk = blk.numpy() if torch.is_tensor(blk) else np.asarray(blk)
+        host = _host_matrix_pointer(np.ascontiguousarray(blk, dtype=np.float32))
+        col_hi, col_lo = col_hi - col_lo, 0
+    addr, ld_src, keep = host
+    n_cells = int(X.shape[0])
+    width = int(col_hi - col_lo)
+    n_sel = width if gene_idx_rel is None else len(gene_idx_rel)
+    ld = (n_sel + 3) // 4 * 4
+    cur = torch.cuda.current_stream()
+    cs = _copy_stream(device)
+    src = ctypes.c_void_p(addr)
+    if row_order is None and gene_idx_rel is None:
+        out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
+        if ld != n_sel:
+            out[:, n_sel:].zero_()
+        cs.wait_stream(cur)
+        rows_per = max(1, int(chunk_bytes // max(4 * width, 1)))
+        for r0 in range(0, n_cells, rows_per):   # a few large strided copies
+            rows = min(rows_per, n_cells - r0)
+            _lib.check(lib.g2g_upload_block(src, ld_src, r0, rows, col_lo, width, ctypes.c_void_p(out[r0].data_ptr()), ld,
+                                            ctypes.c_void_p(cs.cuda_stream)), "g2g_upload_block")
+        cur.wait_stream(cs)
+        out._g2g_keep = keep   # the host block must outlive the asynchronous copies
+        return out
+    out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
+    small = {}
+    if row_order is not None:
+        rank = np.empty(n_cells, dtype=np.int64)
+        rank[np.asarray(row_order)] = np.arange(n_cells, dtype=np.int64)
+        small["rank"] = rank
+    else:
+        small["rank"] = np.arange(n_cells, dtype=np.int64)
+    if gene_idx_rel is not None:
+        small["gi"] = np.asarray(gene_idx_rel, dtype=np.int32)
+    small = upload_small(small, device)
+    rank_dev, gi = small["rank"], small.get("gi")
+    rows_per = max(256, int(chunk_bytes // max(4 * width, 1)))
+    rows_per = min(rows_per, n_cells)
+    stage = [torch.empty((rows_per, width), dtype=torch.float32, device=device) for _ in range(2)]
+    freed = [None, None]
+    cs.wait_stream(cur)
+    for k, r0 in enumerate(range(0, n_cells, rows_per)):
+        rows = min(rows_per, n_cells - r0)
+        buf = stage[k & 1]
+        if freed[k & 1] is not None:
+            cs.wait_event(freed[k & 1])
+        _lib.check(lib.g2g_upload_block(src, ld_src, r0, rows, col_lo, width, _ptr(buf), width,
+                                        ctypes.c_void_p(cs.cuda_stream)), "g2g_upload_block")
+        landed = torch.cuda.Event()
+        landed.record(cs)
+        cur.wait_event(landed)
+        _lib.check(lib.g2g_scatter_rows(_ptr(buf), rows, n_sel, width, ctypes.c_void_p(rank_dev[r0:].data_ptr()), _ptr(gi),
+                                        _ptr(out), ld, _stream()), "g2g_scatter_rows")
+        done = torch.cuda.Event()
+        done.record(cur)
+        freed[k & 1] = done
+    for b in stage:   # the staging chunks are reused by the allocator only after the scatter kernels read them
+        b.record_stream(cur)
+    out._g2g_keep = keep
+    return out
+
+
 def pack_csr(csr, row_order, gene_idx, n_all_genes, device):
     """Densify a scipy CSR matrix (cells x all genes) on the device (``g2g_pack_csr``): only the
     non-zeros cross PCIe."""
@@ -286,6 +383,29 @@ def pack_csc(csr, row_order, gene_idx, n_all_genes, device):
     return CscMatrix(col_ptr, (key % n_cells).to(torch.int32), vals[perm].contiguous(), n_cells, n_genes)
 
 
+def result_shapes(n_rows, n_bins):
+    """name -> (shape, dtype) of the per-gene result arrays for ``n_rows`` genes."""
+    C, T = int(n_rows), int(n_bins)
+    return {"opt_cost": ((C,), torch.float64), "trends": ((C, 4, T), torch.float64),
+            "musigma": ((C, 4, T), torch.float64), "align_len": ((C,), torch.int32),
+            "flags": ((C,), torch.int32), "nnz": ((C, 2), torch.int32),
+            "align_str": ((C, 2 * T), torch.uint8), "l_states": ((C, (T + 1) * (T + 1)), torch.uint8)}
+
+
+def unpack_results(raw, n_rows, n_bins, n_valid=None):
+    """Views of a packed result buffer (numpy u8, laid out for ``n_rows`` genes): name -> array of the
+    first ``n_valid`` genes."""
+    shapes = result_shapes(n_rows, n_bins)
+    host, off = {}, 0
+    for k in AlignmentEngine.RESULT_KEYS:
+        shape, dt = shapes[k]
+        n = int(np.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        arr = raw[off:off + n].view(_NP_DTYPES[dt]).reshape(shape)
+        host[k] = arr if n_valid is None else arr[:n_valid]
+        off += n
+    return host
+
+
 class AlignmentEngine:
     """Runs the whole hot path for one (reference, query) pair of packed device matrices.
 
@@ -298,9 +418,10 @@ class AlignmentEngine:
     MMA_MIN_BINS = 30
 
     def __init__(self, X_ref, tau_ref, X_query, tau_query, n_genes, n_bins, denom_ref, denom_query,
-                 free_params=(0.99, 0.1, 0.7), device=None, moments="auto"):
+                 free_params=(0.99, 0.1, 0.7), device=None, moments="auto", capacity=None):
         """``moments``: ``"auto"`` (tensor cores from ``MMA_MIN_BINS`` interpolation points, else the FFMA2
-        kernel), ``"mma"`` or ``"ffma"``."""
+        kernel), ``"mma"`` or ``"ffma"``.  ``capacity`` (>= n_genes): rows the packed result arrays are
+        laid out for, so that ranks with different gene counts share one record layout (multi-GPU gather)."""
         self.lib = _lib.load()
         _lib.check(self.lib.g2g_check_device(), "g2g_check_device")
         self.device = device if device is not None else X_ref.device
@@ -334,16 +455,17 @@ class AlignmentEngine:
         self.c_model = model_constant()
         # every per-gene result lives in ONE packed byte buffer (8-, 4-, then 1-byte element types, so
         # each view is aligned): the device->host copy and the multi-GPU gather move it as it is
-        shapes = {"opt_cost": ((G,), torch.float64), "trends": ((G, 4, T), torch.float64),
-                  "musigma": ((G, 4, T), torch.float64), "align_len": ((G,), torch.int32),
-                  "flags": ((G,), torch.int32), "nnz": ((G, 2), torch.int32),
-                  "align_str": ((G, 2 * T), torch.uint8), "l_states": ((G, (T + 1) * (T + 1)), torch.uint8)}
+        self.capacity = C = int(capacity) if capacity is not None else G
+        if C < G:
+            raise ValueError("capacity must be >= n_genes")
+        shapes = result_shapes(C, T)
         sizes = [int(np.prod(shapes[k][0])) * torch.empty((), dtype=shapes[k][1]).element_size()
                  for k in self.RESULT_KEYS]
-        self.packed = torch.empty(max(sum(sizes), 8), dtype=torch.uint8, device=dev)
+        self.packed = torch.zeros(max(sum(sizes), 8), dtype=torch.uint8, device=dev)
         off = 0
         for k, n in zip(self.RESULT_KEYS, sizes):
-            setattr(self, k, self.packed[off:off + n].view(shapes[k][1]).reshape(shapes[k][0]))
+            full = self.packed[off:off + n].view(shapes[k][1]).reshape(shapes[k][0])
+            setattr(self, k, full[:G])     # the kernels write the first G rows
             off += n
         self._bind_sides()
         self.fix_ws_bytes = self.lib.g2g_fixup_workspace_bytes(G, T)
@@ -490,16 +612,11 @@ class AlignmentEngine:
                 self.run_interpolation(with_dp=True)
                 self.begin_results_to_host()
                 return self.finish_results_to_host()
-        parts, self._pending_parts = self._pending_parts, None
+        self._pending_parts = None
         raw = self._host_buf.numpy().copy()
         _give_pinned(self._host_buf)
         self._host_buf = None
-        host, off = {}, 0
-        for k, t in zip(self.RESULT_KEYS, parts):
-            n = t.numel() * t.element_size()
-            host[k] = raw[off:off + n].view(_NP_DTYPES[t.dtype]).reshape(tuple(t.shape))
-            off += n
-        return host
+        return unpack_results(raw, self.capacity, self.n_bins, self.n_genes)
 
 
 _PINNED = {}      # n_bytes -> [pinned buffer, event of the last copy that read or wrote it]  (upload staging)

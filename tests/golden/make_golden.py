@@ -27,7 +27,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
 
-import ref_harness as rh  # noqa: E402
+from baseline import ref_runner as rh  # noqa: E402
 from _h5lite import read_h5ad_minimal  # noqa: E402
 from genes2genes_b200 import synthetic  # noqa: E402
 

@@ -205,11 +205,65 @@ def test_result_gather_world_size_2_gloo(tmp_path):
 
 def test_shard_range_covers_all_genes():
     from genes2genes_b200 import distributed as d
-    for G in (1, 7, 8, 1371, 20000):
+    for G in (0, 1, 3, 7, 8, 9, 49, 1371, 20000):
         for world in (1, 2, 4, 8):
             spans = [d.shard_range(G, r, world) for r in range(world)]
             assert spans[0][0] == 0 and spans[-1][1] == G
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            # balanced: no rank is empty while another holds two genes (G = 49 or 7 on 8 ranks, 9 on 4)
+            assert max(sizes) - min(sizes) <= 1
+            assert max(sizes) == d.max_shard(G, world)
+            if G >= world:
+                assert min(sizes) >= 1
+
+
+def test_trajectory_interpolator_reference_signature_and_sorted_names():
+    """``TrajectoryInterpolator(adata, n_bins, ...)`` like the reference (TSP.py:18); cells, their names
+    and the weight-matrix columns are in pseudotime order (TSP.py:20, 51, 129)."""
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    rng = np.random.default_rng(0)
+    X = rng.random((6, 3)).astype(np.float32)
+    t = np.array([0.9, 0.1, 0.5, 0.0, 1.0, 0.3])
+    names = ["c%d" % i for i in range(6)]
+    ad = AnnDataLite(X, t, ["a", "b", "c"], names)
+    ti = TrajectoryInterpolator(ad, 4, adaptive_kernel=False).run()
+    assert list(ti.obs_names) == ["c3", "c1", "c5", "c2", "c0", "c4"]
+    assert list(ti.gene_list) == ["a", "b", "c"]
+    W = ti.cell_weight_mat
+    assert list(W.columns) == list(ti.obs_names)
+    # the column of cell c0 (time 0.9) holds exp(-(0.9 - p)^2 / 0.1^2)
+    np.testing.assert_allclose(W["c0"].values, np.exp(-(0.9 - np.linspace(0, 1, 4)) ** 2 / 0.1 ** 2), rtol=1e-12)
+    assert ti.mat.shape == (3, 6)
+    np.testing.assert_array_equal(np.asarray(ti.mat.todense()), X[np.argsort(t)].T)
+    # from a bare pseudotime array (what the device path uses) there is no .mat
+    with pytest.raises(AttributeError):
+        TrajectoryInterpolator(t, 4, adaptive_kernel=False).mat
+
+
+def test_mma_layout_and_table_size():
+    lay = _lib.mma_layout(100000, 50)
+    assert (lay.n_groups, lay.bins_per_group, lay.n_cols) == (1, 50, 64)
+    assert lay.n_pad == 100032 and lay.cells_per_item == 4096 and lay.n_split == 25
+    assert lay.table_bytes == (100032 // 64) * (64 * 256 + 256)
+    lay = _lib.mma_layout(1500, 100)
+    assert (lay.n_groups, lay.bins_per_group, lay.n_cols) == (2, 50, 64)
+    lay = _lib.mma_layout(700, 30)
+    assert lay.n_cols == 32 and lay.cells_per_item == 704 and lay.n_split == 1
+
+
+def test_reference_runner_when_the_reference_is_present():
+    """baseline/ref_runner.py runs the unmodified package (build container: /root/reference; GPU box:
+    baseline/_ref) and agrees with the oracle's canonical strings."""
+    from baseline import ref_runner
+    if not ref_runner.reference_available():
+        pytest.skip("reference package not present")
+    from genes2genes_b200 import synthetic
+    Xr, tr, Xq, tq, _ = synthetic.make_pair(3, 300, 250, dropout=0.8, seed=11)
+    dt, strs = ref_runner.time_reference(Xr, tr, Xq, tq, 8)
+    want = o.align_batch(Xr, Xq, tr, tq, 8)["alignment_str"]
+    assert dt > 0 and len(strs) == 3
+    assert [o.canonical_gap_blocks(a) for a in strs] == [o.canonical_gap_blocks(b) for b in want]
 
 
 def test_average_alignment_walk_matches_reference(golden_dir):
@@ -278,7 +332,7 @@ def test_bench_reference_arm_prints_one_contract_line():
     the keys of the measurement contract; library chatter must not reach stdout."""
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
-                          "--warmup", "0", "--cpu-genes", "4", "--workload", "C1"],
+                          "--warmup", "0", "--cpu-genes-per-core", "1", "--workload", "C1"],
                          capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
@@ -289,5 +343,7 @@ def test_bench_reference_arm_prints_one_contract_line():
         assert key in d, key
     assert d["impl"] == "reference" and d["metric"] == "gene_alignments_per_sec" and d["unit"] == "genes/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and "workload" in d["config"]
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    # the unmodified package when it is present (build container: /root/reference, GPU box: baseline/_ref)
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["cpu_baseline"]["sequential_value"] > 0 and d["scaling"] == "strong"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
