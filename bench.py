@@ -275,6 +275,15 @@ def ncu_traffic(key):
         return None
 
 
+def fused_ncu(name):
+    """issue / occupancy counters of the fused fix-up + DP launch from the committed ncu capture, if any."""
+    path = os.path.join(ROOT, "profiles", "fused_launch_ncu.json")
+    try:
+        return json.load(open(path)).get(name, {})
+    except Exception:
+        return {}
+
+
 def result_digest(host):
     """sha256 over every gene's integer results and optimal cost (bitwise shard invariant)."""
     h = hashlib.sha256()
@@ -332,7 +341,7 @@ def time_small_workload(name, dropout, dev, steps, warmup):
     L2 flushed between steps."""
     import torch
     G, nr, nq, T = shapes(name)
-    w = DeviceWorkload(name, dropout, 0, G, dev)
+    w = DeviceWorkload(name, dropout, 0, G, dev, keep_raw=True)
     eng = w.engine
     eng.run()
     torch.cuda.synchronize()
@@ -350,15 +359,44 @@ def time_small_workload(name, dropout, dev, steps, warmup):
     for a, b in k1:
         flush.fill_(3)
         eng.time_moments(a, b)
+    fu = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    for a, b in fu:
+        flush.fill_(4)
+        eng.time_fused(a, b)
     torch.cuda.synchronize()
     ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
     k1_ms = float(np.mean([a.elapsed_time(b) for a, b in k1]))
+    fu_ms = float(np.mean([a.elapsed_time(b) for a, b in fu]))
     peak, _ = measured_peak()
     alg = 4.0 * (nr + nq) * G + 8.0 * (nr + nq)
-    return {"workload": config_dict(name, dropout, 1)["workload"], "ms_per_step": ms, "value": G / (ms * 1e-3),
-            "unit": UNIT, "steps": steps, "l2": "flushed (256 MiB write) between steps", "cuda_graph": graph is not None,
-            "kernel": "moments_mma_kernel" if eng.variant == "mma" else "moments_kernel", "kernel_ms": k1_ms,
-            "roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peak}
+    out = {"workload": config_dict(name, dropout, 1)["workload"], "ms_per_step": ms, "value": G / (ms * 1e-3),
+           "unit": UNIT, "steps": steps, "l2": "flushed (256 MiB write) between steps", "cuda_graph": graph is not None,
+           "kernel": "moments_mma_kernel" if eng.variant == "mma" else "moments_kernel", "kernel_ms": k1_ms,
+           "roofline_frac": alg / (k1_ms * 1e-3) / 1e9 / peak, "fused_fixup_dp_ms": fu_ms}
+    # end to end through the public API from pinned host matrices (original cell order) to host result objects
+    from genes2genes_b200 import Main
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    Xr, Xq = w.raw
+    Xr_pin = torch.empty(Xr.shape, dtype=torch.float32, pin_memory=True); Xr_pin.copy_(Xr)
+    Xq_pin = torch.empty(Xq.shape, dtype=torch.float32, pin_memory=True); Xq_pin.copy_(Xq)
+    torch.cuda.synchronize()
+    w.raw = None
+    ar = AnnDataLite(Xr_pin[:, :G], w.tr, w.genes)
+    aq = AnnDataLite(Xq_pin[:, :G], w.tq, w.genes)
+    e2e = []
+    for k in range(6):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        al = Main.RefQueryAligner(ar, aq, w.genes, T, verbose=False)
+        al.align_all_pairs()
+        n = sum(a.alignment_str.count("M") for a in al.results)
+        torch.cuda.synchronize()
+        if k:
+            e2e.append((time.perf_counter() - t0) * 1e3)
+        del al
+    out["e2e"] = {"value": G / (float(np.mean(e2e)) * 1e-3), "unit": UNIT, "ms_per_step": float(np.mean(e2e)),
+                  "ms_each": [round(v, 3) for v in e2e], "h2d_bytes_per_step": int(4 * (nr + nq) * G + 8 * (nr + nq))}
+    return out
 
 
 def run_b200(args):
@@ -449,6 +487,11 @@ def run_b200(args):
     torch.cuda.synchronize()
     k1_ms = [a.elapsed_time(b) for a, b in k1_events]
     # the fused fix-up + DP launch alone
+    fu_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in fu_events:
+        eng.time_fused(a, b)
+    torch.cuda.synchronize()
+    fu_ms = float(np.mean([a.elapsed_time(b) for a, b in fu_events]))
     clocks = sampler.finish() if rank == 0 else None
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
@@ -534,6 +577,9 @@ def run_b200(args):
                          "tensor": {"flops_per_launch": 2.0 * 3 * 2 * 64 * (nr + nq) * n_loc,
                                     "note": "six f16 MMAs (M 128, N 64, K 16) per 16 cells x 128 genes; the tensor "
                                             "pipe is not the bound"} if mma else None},
+            "fused_fixup_dp": dict({"kernel": "fixup_dp_kernel (K3 + K4 g2g_fixup_cost_dp)", "kernel_ms": fu_ms,
+                                    "kernel_share_of_step": fu_ms / ms_per_step, "bound": "latency (one warp per gene, "
+                                    "2T+1 dependent wavefront steps)"}, **fused_ncu(args.workload)),
             "result_sha256_24": digest,
             "shard_check": shard_check,
             "clocks": clocks,

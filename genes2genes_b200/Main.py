@@ -484,24 +484,28 @@ class RefQueryAligner:
         self.no_extreme_cases = False
 
         k = 1
-        self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
-            self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
-            obs_names=getattr(adata_ref, "obs_names", None)).run()
-        self.TrajInt_Q = TimeSeriesPreprocessor.TrajectoryInterpolator(
-            self.query_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
-            obs_names=getattr(adata_query, "obs_names", None)).run()
         try:
             import scipy.sparse as _sp
             self._both_sparse = _sp.issparse(adata_ref.X) and _sp.issparse(adata_query.X)
         except Exception:
             self._both_sparse = False
         self._engine = None
-        if len(self._local_genes) > 0:   # a rank of a multi-GPU job may own no gene at all (fewer genes than ranks)
-            with torch.cuda.device(self.device):
-                # the host->device copies are asynchronous: the second dataset is packed, the weight tables and
-                # the engine's buffers are set up while the DMA engine streams the first
-                Xr = self._pack(adata_ref, self.TrajInt_R.order)
-                Xq = self._pack(adata_query, self.TrajInt_Q.order)
+        has_genes = len(self._local_genes) > 0   # a rank of a multi-GPU job may own no gene (fewer genes than ranks)
+        # Order matters for the end-to-end time: the pseudotime sort of a dataset is all its upload needs, so each
+        # host->device stream is started first and the kernel-width computation, the second dataset and the
+        # engine's buffers are set up while the DMA engine works.
+        with torch.cuda.device(self.device):
+            self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
+                self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
+                obs_names=getattr(adata_ref, "obs_names", None))
+            Xr = self._pack(adata_ref, self.TrajInt_R.order) if has_genes else None
+            self.TrajInt_Q = TimeSeriesPreprocessor.TrajectoryInterpolator(
+                self.query_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
+                obs_names=getattr(adata_query, "obs_names", None))
+            Xq = self._pack(adata_query, self.TrajInt_Q.order) if has_genes else None
+            self.TrajInt_R.run()
+            self.TrajInt_Q.run()
+            if has_genes:
                 if isinstance(Xr, _engine.CscMatrix) != isinstance(Xq, _engine.CscMatrix):
                     # one side fell over the density threshold: densify the sparse one too
                     self._both_sparse = False
@@ -529,14 +533,13 @@ class RefQueryAligner:
         local genes need to be present in ``adata`` -- a rank of a multi-GPU job may load just its block."""
         var_names = adata.var_names
         local = self._local_genes
-        n_var = len(var_names)
-        if n_var == len(local) and all(str(a) == b for a, b in zip(var_names, local)):
-            return 0, n_var, None
-        pos = {str(g): k for k, g in enumerate(var_names)}
-        try:
-            cols = np.asarray([pos[g] for g in local], dtype=np.int64)
-        except KeyError as exc:
-            raise KeyError("gene %s of gene_list is not in var_names" % exc) from None
+        if hasattr(var_names, "get_indexer"):          # pandas Index: one vectorised hash lookup
+            cols = np.asarray(var_names.get_indexer(local), dtype=np.int64)
+        else:
+            pos = {str(g): k for k, g in enumerate(var_names)}
+            cols = np.asarray([pos.get(g, -1) for g in local], dtype=np.int64)
+        if len(cols) and cols.min() < 0:
+            raise KeyError("gene %r of gene_list is not in var_names" % local[int(np.argmin(cols))])
         lo, hi = int(cols.min()), int(cols.max()) + 1
         if hi - lo == len(cols) and np.array_equal(cols, np.arange(lo, hi)):
             return lo, hi, None

@@ -41,10 +41,17 @@ class TrajectoryInterpolator:
         self.adaptive_kernel = adaptive_kernel
         self.k = raising_degree
         self.gene_list = gene_list
-        # cells are kept in pseudotime order (TimeSeriesPreprocessor.py:20): so are their names
-        self.obs_names = None if obs_names is None else np.asarray(obs_names)[self.order]
+        self._obs_names_in = obs_names
+        self._obs_names = None
         self._weights = None
         self._mat = None
+
+    @property
+    def obs_names(self):
+        """Cell names in pseudotime order, like the cells themselves (TimeSeriesPreprocessor.py:20)."""
+        if self._obs_names is None and self._obs_names_in is not None:
+            self._obs_names = np.asarray(self._obs_names_in)[self.order]
+        return self._obs_names
 
     @property
     def adata(self):

@@ -7,8 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-# G2G_LIBRARY selects another build of the same library (kernel tuning experiments)
-LIB_PATH = os.environ.get("G2G_LIBRARY") or os.path.join(_HERE, "libg2g.so")
+LIB_PATH = os.path.join(_HERE, "libg2g.so")
 
 c_i32, c_i64, c_f64, c_vp, c_sz = ctypes.c_int32, ctypes.c_int64, ctypes.c_double, ctypes.c_void_p, ctypes.c_size_t
 

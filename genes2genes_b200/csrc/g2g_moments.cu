@@ -92,10 +92,9 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-#ifndef G2G_MOM_MIN_BLOCKS
-#define G2G_MOM_MIN_BLOCKS 2   // CTAs per SM the register / shared-memory budget is sized for (tuning knob;
-                               // 2 measured faster than 1 on B200, profiles/r01_k1_item_size_sweep.txt)
-#endif
+// CTAs per SM the register / shared-memory budget is sized for (2 measured faster than 1 on B200,
+// profiles/r01_k1_item_size_sweep.txt)
+constexpr int kMomMinBlocks = 2;
 
 template <int TBE, int GX>
 struct Cfg {
@@ -108,7 +107,7 @@ struct Cfg {
   static constexpr int STAGE_BYTES = XBYTES + WBYTES;
   // the cross-warp reduction goes through a shared staging area, in kPasses slices of kRows rows
   // two CTAs per SM while the register tile leaves room (<= 128 registers without spills)
-  static constexpr int kMinBlocks = (G2G_MOM_MIN_BLOCKS >= 2 && 2 * TBE * GX <= 64) ? 2 : 1;
+  static constexpr int kMinBlocks = (kMomMinBlocks >= 2 && 2 * TBE * GX <= 64) ? 2 : 1;
   static constexpr int kStagingCap = (kMinBlocks >= 2 ? 16 : 64) * 1024;
   static constexpr int kPasses = (kConsumerWarps * NQ * GT * 4 + kStagingCap - 1) / kStagingCap;
   static constexpr int kRows = (NQ + kPasses - 1) / kPasses;
@@ -486,7 +485,7 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
   G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const size_t fixed = (size_t)C::STAGING_BYTES + (size_t)C::NQ * C::GT * 8 + (size_t)p.n_bins * C::GT * 4 +
                        8 * 8 + (8 + kCursorInts) * 4 + 128;
-  // as many stages (<= 8, >= 2) as fit the shared memory of G2G_MOM_MIN_BLOCKS CTAs per SM
+  // as many stages (<= 8, >= 2) as fit the shared memory of kMomMinBlocks CTAs per SM
   int stages = 8;
   const size_t budget = (size_t)(C::kMinBlocks >= 2 ? 110 : 200) * 1024;
   while (stages > 2 && fixed + (size_t)stages * C::STAGE_BYTES > budget) --stages;
@@ -500,10 +499,6 @@ int launch_moments(MomParams& p, const g2g_side_t* sides, cudaStream_t stream) {
     return G2G_ERR_UNSUPPORTED;
   }
   int grid = n_sm * occ;
-  if (const char* env = getenv("G2G_MOM_CTAS_PER_SM")) {  // tuning knob
-    int v = atoi(env);
-    if (v >= 1 && v <= occ) grid = n_sm * v;
-  }
   if (grid > items) grid = items;
   moments_kernel<TBE, GX><<<grid, kThreads, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());

@@ -217,10 +217,6 @@ extern "C" int g2g_layout(int64_t n_cells, int32_t n_bins, g2g_layout_t* out) {
   int64_t min_item = g2g_round_up(12 * (5 * (int64_t)t.bins_per_group + 2), G2G_CELL_TILE);
   int64_t by_n = g2g_round_up(g2g_ceil_div(n_cells, 64), G2G_CELL_TILE);
   int64_t item = by_n > min_item ? by_n : min_item;
-  if (const char* env = getenv("G2G_ITEM_CELLS")) {  // tuning knob (must be the same for every call of a run)
-    int64_t v = atoll(env);
-    if (v >= G2G_CELL_TILE) item = g2g_round_up(v, G2G_CELL_TILE);
-  }
   if (item > out->n_pad) item = out->n_pad;
   out->cells_per_item = item;
   out->n_split = g2g_ceil_div(out->n_pad, item);

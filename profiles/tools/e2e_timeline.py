@@ -9,7 +9,9 @@ import bench
 from genes2genes_b200 import Main
 from genes2genes_b200.anndata_lite import AnnDataLite
 
-Xr, tr, Xq, tq, genes, T = bench.workload("C2", 0.9)
+from genes2genes_b200 import synthetic
+_G, _nr, _nq, T = synthetic.CONFIGS["C2"]
+Xr, tr, Xq, tq, genes = synthetic.make_pair(_G, _nr, _nq, dropout=0.9, seed=100)
 ar = AnnDataLite(torch.from_numpy(Xr).pin_memory(), tr, genes)
 aq = AnnDataLite(torch.from_numpy(Xq).pin_memory(), tq, genes)
 
