@@ -431,8 +431,12 @@ class RefQueryAligner:
 
     #: scipy-sparse inputs at most this dense stay sparse on the device (K1s: work and memory ~ stored
     #: entries; measured break-even with the dense kernel near 9 % on B200); denser
-    #: ones are densified on the device and streamed by K1.  Set to 1.0 to force the sparse path when the
-    #: dense matrix would not fit in HBM.
+    #: ones are densified on the device and streamed by K1 / K1m.  Precision: K1s sums ``w x^2`` un-shifted
+    #: in f32, so the relative error of a bin's variance is about 1e-7 * (1 + mean^2 / variance).  At or below
+    #: the default threshold mean^2 / variance is bounded by the density itself (a mostly-zero column), so the
+    #: sparse path is as accurate as the dense one; raising the threshold (1.0 forces the sparse path, e.g.
+    #: when the dense matrix would not fit in HBM) is only safe for data whose columns are not "high mean,
+    #: low variance" -- dense, nearly constant genes lose variance digits to cancellation there.
     sparse_density_threshold = 0.08
 
     def __init__(self, *args, device=None, verbose=True, distributed=False):

@@ -59,9 +59,11 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 // Wrapping counter: returns the old value and stores old >= limit ? 0 : old + 1.  The arrival that sees
 // `limit` has also reset the counter, and ptxas emits a bare ATOMS.INC for it (an ATOMS.ADD gets wrapped
 // in warp-aggregation code even when a single lane runs it).
+// acq_rel at CTA scope: the arrival that completes a stage (and goes on to overwrite it) is ordered after the
+// other warps' shared-memory reads of that stage, which their own arrivals released.
 __device__ __forceinline__ unsigned smem_atomic_inc_wrap(int* addr, unsigned limit) {
   unsigned old;
-  asm volatile("atom.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(limit) : "memory");
+  asm volatile("atom.acq_rel.cta.shared.inc.u32 %0, [%1], %2;" : "=r"(old) : "r"(smem_u32(addr)), "r"(limit) : "memory");
   return old;
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
@@ -410,8 +412,12 @@ __global__ void __launch_bounds__(kThreads, Cfg<TBE, GX>::kMinBlocks) moments_ke
       }
       __syncwarp();  // every lane's shared-memory reads of this stage have returned (values are in registers)
       if (lane == 0) {
-        // last warp out refills the stage (its arrival also wraps the counter back to 0)
-        if (smem_atomic_inc_wrap(&done[slot], kConsumerWarps - 1) == kConsumerWarps - 1) issue_next(slot);
+        // last warp out refills the stage (its arrival also wraps the counter back to 0); the proxy fence orders
+        // the generic-proxy reads of the stage before the async-proxy (TMA / bulk copy) writes that reuse it
+        if (smem_atomic_inc_wrap(&done[slot], kConsumerWarps - 1) == kConsumerWarps - 1) {
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          issue_next(slot);
+        }
       }
       if (++slot == n_stages) { slot = 0; phase ^= 1; }
       if (++since_flush == kFlushStages && tile + 1 < it.n_tiles) { reduce_flush(false, it); since_flush = 0; }

@@ -133,6 +133,12 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
       "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(4000u)
       : "memory");
 }
+// Blocking hardware barrier among `threads` threads (id 1..15; 0 is __syncthreads): a waiting warp issues
+// nothing, unlike a warp polling an mbarrier.  Roles whose warps all wait for the same mbarrier let one warp
+// poll it and meet the others here.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -391,7 +397,8 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
       for (int j = 0; j < N; ++j) acc[j] = 0.0f;
       for (int c = 0; c < chains; ++c, ++n_chain) {
         const uint32_t accb = n_chain & 1;
-        mbar_wait_relaxed(&acc_full[accb], (n_chain >> 1) & 1);
+        if (warp == kFirstFlushWarp) mbar_wait_relaxed(&acc_full[accb], (n_chain >> 1) & 1);
+        named_bar_sync(1, kFlushWarps * 32);
         tc_fence_after();
         const uint32_t src = lane_base + accb * (2 * N) + h * N;
 #pragma unroll
@@ -407,7 +414,11 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
         if (lane == 0) mbar_arrive(&acc_empty[accb]);
       }
       // item end: add the lo accumulator, write the f64 partial sums of this (item, gene)
-      mbar_wait_relaxed(lo_full, n_item & 1);
+      if (warp == kFirstFlushWarp) {
+        mbar_wait_relaxed(lo_full, n_item & 1);
+        mbar_wait_relaxed(&c_full[n_item & 1], (n_item >> 1) & 1);
+      }
+      named_bar_sync(1, kFlushWarps * 32);
       tc_fence_after();
       const MmaSide& s = p.side[it.side];
       const long long g = (long long)it.gt * kGT + q * 32 + lane;
@@ -433,7 +444,6 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
       if (lane == 0) mbar_arrive(lo_empty);
       if (h == 0) {   // sum (x - a): the converter groups' shares, added in group order
         const uint32_t par = n_item & 1;
-        mbar_wait_relaxed(&c_full[par], (n_item >> 1) & 1);
         double c = 0.0;
 #pragma unroll
         for (int k = 0; k < kConvGroups; ++k) c += c_s[(par * kConvGroups + k) * kGT + q * 32 + lane];
@@ -488,7 +498,11 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
 #pragma unroll 1
         for (int s4 = 0; s4 < kStepsPerStage; ++s4, ++n_step) {
           if ((int)(n_step % kConvGroups) != cg) continue;
-          if (!waited) { mbar_wait(&stage_full[stage], sph); waited = true; }
+          if (!waited) {
+            if (q == 0) mbar_wait(&stage_full[stage], sph);
+            named_bar_sync(2 + cg, 128);
+            waited = true;
+          }
           const float* xs = xt + (s4 * kStepCells) * kGT + gl;
           int nz = 0;
           unsigned long long csum2 = 0ull;
@@ -511,7 +525,8 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
               split2(mul2(d2, d2), yh[j], yl[j]);
             }
             if (half == 0) {   // the buffer's previous occupants have been consumed by the MMAs
-              mbar_wait(&a_empty[ab], ((n_step / kABufs) & 1) ^ 1);
+              if (q == 0) mbar_wait(&a_empty[ab], ((n_step / kABufs) & 1) ^ 1);
+              named_bar_sync(2 + cg, 128);
               tc_fence_after();
             }
             if (!(G2G_MMA_ABLATE & 8)) {

@@ -706,6 +706,35 @@ def test_sparse_csc_path_equals_dense_path(T):
             assert abs(a_obj.fwd_DP.opt_cost - dense["opt_cost"][g]) <= 5e-5 * abs(dense["opt_cost"][g])
 
 
+def test_dense_high_mean_low_variance_csr_input_keeps_its_variance_digits():
+    """A fully dense, nearly constant matrix handed over as scipy CSR (mean^2 / variance ~ 1e4): under the
+    default density threshold the aligner densifies it on the device and the shifted single-pass variance of
+    the dense kernels keeps the stds within tolerance of the f64 oracle (the un-shifted sparse kernel would
+    lose four digits here, which is why it is only chosen for mostly-zero data)."""
+    import scipy.sparse as sp
+    from genes2genes_b200 import Main
+    from genes2genes_b200.anndata_lite import AnnDataLite
+    rng = np.random.default_rng(8)
+    G, nr, nq, T = 40, 1500, 1300, 14
+    tr, tq = rng.uniform(0, 1, nr), rng.uniform(0, 1, nq)
+    tr[0], tr[1], tq[0], tq[1] = 0.0, 1.0, 0.0, 1.0
+    base = rng.uniform(5.0, 9.0, G)
+    Xr = (base[None, :] + 0.05 * np.sin(6 * tr)[:, None] + rng.normal(0, 0.05, (nr, G))).astype(np.float32)
+    Xq = (base[None, :] + 0.05 * np.cos(5 * tq)[:, None] + rng.normal(0, 0.05, (nq, G))).astype(np.float32)
+    genes = ["g%d" % i for i in range(G)]
+    al = Main.RefQueryAligner(AnnDataLite(sp.csr_matrix(Xr), tr, genes), AnnDataLite(sp.csr_matrix(Xq), tq, genes),
+                              genes, T, verbose=False)
+    assert not al._engine.sparse                      # density 1.0 > sparse_density_threshold: densified
+    al.align_all_pairs()
+    ref = o.align_batch(Xr, Xq, tr, tq, T)
+    h = al._host
+    for k, key in enumerate(("mu_S", "sd_S", "mu_T", "sd_T")):
+        want = ref[key]
+        assert (np.abs(h["musigma"][:, k] - want) / np.abs(want)).max() < RTOL_MOMENTS, key
+    got = [a.alignment_str for a in al.results]
+    assert [o.canonical_gap_blocks(s) for s in got] == [o.canonical_gap_blocks(s) for s in ref["alignment_str"]]
+
+
 def test_api_sparse_inputs_of_mixed_density_are_both_densified():
     """Two scipy-sparse inputs on different sides of ``sparse_density_threshold``: the sparse K1s
     needs both sides in CSC form, so the aligner densifies both on the device and the results are
