@@ -499,14 +499,16 @@ class RefQueryAligner:
         # host->device stream is started first and the kernel-width computation, the second dataset and the
         # engine's buffers are set up while the DMA engine works.
         with torch.cuda.device(self.device):
+            up_r = self._begin_pack(adata_ref) if has_genes else None      # PCIe starts before the time sort
             self.TrajInt_R = TimeSeriesPreprocessor.TrajectoryInterpolator(
                 self.ref_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
                 obs_names=getattr(adata_ref, "obs_names", None))
-            Xr = self._pack(adata_ref, self.TrajInt_R.order) if has_genes else None
+            Xr = self._pack(adata_ref, self.TrajInt_R.order, up_r) if has_genes else None
+            up_q = self._begin_pack(adata_query) if has_genes else None
             self.TrajInt_Q = TimeSeriesPreprocessor.TrajectoryInterpolator(
                 self.query_time, n_bins, adaptive_kernel=adaptive_kernel, raising_degree=k, gene_list=gene_list,
                 obs_names=getattr(adata_query, "obs_names", None))
-            Xq = self._pack(adata_query, self.TrajInt_Q.order) if has_genes else None
+            Xq = self._pack(adata_query, self.TrajInt_Q.order, up_q) if has_genes else None
             self.TrajInt_R.run()
             self.TrajInt_Q.run()
             if has_genes:
@@ -549,12 +551,32 @@ class RefQueryAligner:
             return lo, hi, None
         return lo, hi, (cols - lo).astype(np.int32)
 
-    def _pack(self, adata, order):
+    def _begin_pack(self, adata):
+        """Start the host->device stream of a dense host ``adata.X`` (None for sparse / device inputs, which
+        ``_pack`` handles in one go): the first chunks are in flight while the caller sorts the pseudotimes."""
+        import torch
+        X = adata.X
+        try:
+            import scipy.sparse as sp
+            if sp.issparse(X):
+                return None
+        except Exception:
+            pass
+        if hasattr(X, "todense") and not hasattr(X, "__array_interface__") and not hasattr(X, "data_ptr"):
+            return None
+        if isinstance(X, np.matrix) or (torch.is_tensor(X) and X.device.type == "cuda"):
+            return None
+        col_lo, col_hi, idx = self._local_columns(adata)
+        return _engine.HostBlockUpload(X, col_lo, col_hi, idx, self.device).start()
+
+    def _pack(self, adata, order, started=None):
         """``adata[order][:, gene_list].X`` as a packed f32 device matrix (or a ``CscMatrix``)."""
         import torch
+        identity = bool(np.all(order[1:] > order[:-1])) if len(order) > 1 else True
+        if started is not None:
+            return started.finish(None if identity else order)
         col_lo, col_hi, idx = self._local_columns(adata)
         X = adata.X
-        identity = bool(np.all(order[1:] > order[:-1])) if len(order) > 1 else True
         row_order = None if identity else order
         try:
             import scipy.sparse as sp
@@ -679,21 +701,28 @@ class RefQueryAligner:
             if eng is None:
                 return _engine.unpack_results(np.zeros(send.numel(), dtype=np.uint8), cap, T, 0)
             return eng.results_to_host()
+        host_buf = None
         if on_host:
             raw = recv.numpy()
         else:
             host_buf = _engine._take_pinned(recv.numel())
             host_buf.copy_(recv.view(-1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
-            raw = host_buf.numpy().reshape(world, -1).copy()
-            _engine._give_pinned(host_buf)
-        parts = []
+            raw = host_buf.numpy().reshape(world, -1)
+        # one pass from the (pinned) receive buffer into per-key arrays that cover every gene
+        shapes = _engine.result_shapes(n_all, T)
+        out = {k: np.empty(shapes[k][0], dtype=_engine._NP_DTYPES[shapes[k][1]]) for k in _engine.AlignmentEngine.RESULT_KEYS}
         for r in range(world):
             lo, hi = D.shard_range(n_all, r, world)
-            parts.append(_engine.unpack_results(raw[r], cap, T, hi - lo))
+            if hi > lo:
+                part = _engine.unpack_results(raw[r], cap, T, hi - lo)
+                for k, v in part.items():
+                    out[k][lo:hi] = v
+        if host_buf is not None:
+            _engine._give_pinned(host_buf)
         self.gene_list = self._all_genes                    # rank 0 now holds every gene's result
         self._shard = (0, n_all)
-        return {k: np.concatenate([p[k] for p in parts]) for k in _engine.AlignmentEngine.RESULT_KEYS}
+        return out
 
     def _make_result(self, idx, host=None):
         return AligmentObj(self._store, idx, self.gene_list[idx], host)

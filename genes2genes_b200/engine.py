@@ -232,86 +232,104 @@ def _copy_stream(device):
     return _COPY_STREAMS[key]
 
 
-def upload_host_block(X, row_order, col_lo, col_hi, gene_idx_rel, device, chunk_bytes=96 << 20):
+class HostBlockUpload:
     """Packed device copy of ``X[row_order][:, col_lo:col_hi][:, gene_idx_rel]`` for a HOST matrix ``X``
-    (row-major f32, cells x all genes; ideally pinned): only the column block crosses PCIe, as strided
-    DMA copies of ``chunk_bytes`` (``g2g_upload_block``) on a copy stream, and every chunk is scattered to
-    its time-sorted rows (``g2g_scatter_rows``) while the next one is in flight.  No whole-matrix device
-    copy exists at any time: one [cells x ld] result plus two staging chunks.  ``row_order`` /
-    ``gene_idx_rel`` may be None (identity); with both None the block is copied straight into place."""
-    lib = _lib.load()
-    host = _host_matrix_pointer(X)
-    if host is None:   # other dtypes / layouts: make a f32 host copy of the column block only
-        blk = X[:, col_lo:col_hi]
-        blk = blk.numpy() if torch.is_tensor(blk) else np.asarray(blk)
-        host = _host_matrix_pointer(np.ascontiguousarray(blk, dtype=np.float32))
-        col_hi, col_lo = col_hi - col_lo, 0
-    addr, ld_src, keep = host
-    n_cells = int(X.shape[0])
-    width = int(col_hi - col_lo)
-    n_sel = width if gene_idx_rel is None else len(gene_idx_rel)
-    ld = (n_sel + 3) // 4 * 4
-    cur = torch.cuda.current_stream()
-    cs = _copy_stream(device)
-    src = ctypes.c_void_p(addr)
-    full_rows = col_lo == 0 and width == ld_src   # whole rows: a chunk is one contiguous range of bytes
+    (row-major f32, cells x all genes; ideally pinned), in two steps so that the PCIe stream can start before
+    the pseudotime order of the cells is known:
 
-    def upload(r0, rows, dst_ptr, ld_dst):
-        if full_rows and ld_dst == width:
-            # one 1-D copy: a strided copy of rows that are not 16-byte multiples runs at 2/3 of the PCIe rate
-            _lib.check(lib.g2g_upload_block(ctypes.c_void_p(addr + 4 * r0 * ld_src), rows * ld_src, 0, 1, 0, rows * ld_src,
-                                            dst_ptr, rows * ld_src, ctypes.c_void_p(cs.cuda_stream)), "g2g_upload_block")
+    ``start()`` issues the first chunk copies on a copy stream -- only the column block crosses PCIe, as
+    strided DMA copies of ``chunk_bytes`` (``g2g_upload_block``; whole rows go as 1-D copies) into two staging
+    chunks; ``finish(row_order)`` scatters every chunk to its time-sorted rows (``g2g_scatter_rows``) while
+    the next one is in flight and returns the [cells x ld] matrix.  No whole-matrix second copy exists at any
+    time.  ``row_order`` / ``gene_idx_rel`` may be None (identity)."""
+
+    def __init__(self, X, col_lo, col_hi, gene_idx_rel, device, chunk_bytes=96 << 20):
+        self.lib = _lib.load()
+        host = _host_matrix_pointer(X)
+        if host is None:   # other dtypes / layouts: make a f32 host copy of the column block only
+            blk = X[:, col_lo:col_hi]
+            blk = blk.numpy() if torch.is_tensor(blk) else np.asarray(blk)
+            host = _host_matrix_pointer(np.ascontiguousarray(blk, dtype=np.float32))
+            col_hi, col_lo = col_hi - col_lo, 0
+        self.addr, self.ld_src, self.keep = host
+        self.device = device
+        self.n_cells = int(X.shape[0])
+        self.col_lo, self.width = int(col_lo), int(col_hi - col_lo)
+        self.gene_idx_rel = gene_idx_rel
+        self.n_sel = self.width if gene_idx_rel is None else len(gene_idx_rel)
+        self.ld = (self.n_sel + 3) // 4 * 4
+        # whole rows: a chunk is one contiguous range of bytes (a strided copy of rows that are not 16-byte
+        # multiples runs at 2/3 of the PCIe rate: profiles/tools/upload_timing.py)
+        self.full_rows = self.col_lo == 0 and self.width == self.ld_src
+        self.rows_per = min(max(256, int(chunk_bytes // max(4 * self.width, 1))), self.n_cells)
+        self.cs = _copy_stream(device)
+        self.stage = None
+        self.landed = []          # events of the chunk copies issued so far
+        self.next_chunk = 0
+        self.n_chunks = -(-self.n_cells // self.rows_per)
+
+    def _copy_chunk(self, k):
+        r0 = k * self.rows_per
+        rows = min(self.rows_per, self.n_cells - r0)
+        buf = self.stage[k & 1]
+        cs = ctypes.c_void_p(self.cs.cuda_stream)
+        if self.full_rows:
+            _lib.check(self.lib.g2g_upload_block(ctypes.c_void_p(self.addr + 4 * r0 * self.ld_src), rows * self.ld_src, 0, 1,
+                                                 0, rows * self.ld_src, _ptr(buf), rows * self.ld_src, cs), "g2g_upload_block")
         else:
-            _lib.check(lib.g2g_upload_block(src, ld_src, r0, rows, col_lo, width, dst_ptr, ld_dst,
-                                            ctypes.c_void_p(cs.cuda_stream)), "g2g_upload_block")
+            _lib.check(self.lib.g2g_upload_block(ctypes.c_void_p(self.addr), self.ld_src, r0, rows, self.col_lo, self.width,
+                                                 _ptr(buf), self.width, cs), "g2g_upload_block")
+        ev = torch.cuda.Event()
+        ev.record(self.cs)
+        self.landed.append(ev)
 
-    if row_order is None and gene_idx_rel is None and (ld == n_sel or not full_rows):
-        out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
-        if ld != n_sel:
-            out[:, n_sel:].zero_()
-        cs.wait_stream(cur)
-        rows_per = max(1, int(chunk_bytes // max(4 * width, 1)))
-        for r0 in range(0, n_cells, rows_per):   # a few large strided copies
-            rows = min(rows_per, n_cells - r0)
-            upload(r0, rows, ctypes.c_void_p(out[r0].data_ptr()), ld)
-        cur.wait_stream(cs)
-        out._g2g_keep = keep   # the host block must outlive the asynchronous copies
+    def start(self):
+        if self.stage is None:
+            self.stage = [torch.empty((self.rows_per, self.width), dtype=torch.float32, device=self.device)
+                          for _ in range(min(2, self.n_chunks))]
+            self.cs.wait_stream(torch.cuda.current_stream())
+            while self.next_chunk < min(2, self.n_chunks):
+                self._copy_chunk(self.next_chunk)
+                self.next_chunk += 1
+        return self
+
+    def finish(self, row_order):
+        self.start()
+        cur = torch.cuda.current_stream()
+        n_cells, ld = self.n_cells, self.ld
+        out = torch.empty((n_cells, ld), dtype=torch.float32, device=self.device)
+        if row_order is not None:
+            rank = np.empty(n_cells, dtype=np.int64)
+            rank[np.asarray(row_order)] = np.arange(n_cells, dtype=np.int64)
+        else:
+            rank = np.arange(n_cells, dtype=np.int64)
+        small = {"rank": rank}
+        if self.gene_idx_rel is not None:
+            small["gi"] = np.asarray(self.gene_idx_rel, dtype=np.int32)
+        small = upload_small(small, self.device)
+        rank_dev, gi = small["rank"], small.get("gi")
+        for k in range(self.n_chunks):
+            r0 = k * self.rows_per
+            rows = min(self.rows_per, n_cells - r0)
+            cur.wait_event(self.landed[k])
+            _lib.check(self.lib.g2g_scatter_rows(_ptr(self.stage[k & 1]), rows, self.n_sel, self.width,
+                                                 ctypes.c_void_p(rank_dev[r0:].data_ptr()), _ptr(gi), _ptr(out), ld, _stream()),
+                       "g2g_scatter_rows")
+            if self.next_chunk < self.n_chunks:      # the chunk two ahead reuses this staging buffer
+                done = torch.cuda.Event()
+                done.record(cur)
+                self.cs.wait_event(done)
+                self._copy_chunk(self.next_chunk)
+                self.next_chunk += 1
+        for b in self.stage:   # the staging chunks are reused by the allocator only after the scatter kernels read them
+            b.record_stream(cur)
+        out._g2g_keep = self.keep   # the host block must outlive the asynchronous copies
         return out
-    out = torch.empty((n_cells, ld), dtype=torch.float32, device=device)
-    small = {}
-    if row_order is not None:
-        rank = np.empty(n_cells, dtype=np.int64)
-        rank[np.asarray(row_order)] = np.arange(n_cells, dtype=np.int64)
-        small["rank"] = rank
-    else:
-        small["rank"] = np.arange(n_cells, dtype=np.int64)
-    if gene_idx_rel is not None:
-        small["gi"] = np.asarray(gene_idx_rel, dtype=np.int32)
-    small = upload_small(small, device)
-    rank_dev, gi = small["rank"], small.get("gi")
-    rows_per = max(256, int(chunk_bytes // max(4 * width, 1)))
-    rows_per = min(rows_per, n_cells)
-    stage = [torch.empty((rows_per, width), dtype=torch.float32, device=device) for _ in range(2)]
-    freed = [None, None]
-    cs.wait_stream(cur)
-    for k, r0 in enumerate(range(0, n_cells, rows_per)):
-        rows = min(rows_per, n_cells - r0)
-        buf = stage[k & 1]
-        if freed[k & 1] is not None:
-            cs.wait_event(freed[k & 1])
-        upload(r0, rows, _ptr(buf), width)
-        landed = torch.cuda.Event()
-        landed.record(cs)
-        cur.wait_event(landed)
-        _lib.check(lib.g2g_scatter_rows(_ptr(buf), rows, n_sel, width, ctypes.c_void_p(rank_dev[r0:].data_ptr()), _ptr(gi),
-                                        _ptr(out), ld, _stream()), "g2g_scatter_rows")
-        done = torch.cuda.Event()
-        done.record(cur)
-        freed[k & 1] = done
-    for b in stage:   # the staging chunks are reused by the allocator only after the scatter kernels read them
-        b.record_stream(cur)
-    out._g2g_keep = keep
-    return out
+
+
+def upload_host_block(X, row_order, col_lo, col_hi, gene_idx_rel, device, chunk_bytes=96 << 20):
+    """``HostBlockUpload(...).start().finish(row_order)`` in one call."""
+    return HostBlockUpload(X, col_lo, col_hi, gene_idx_rel, device, chunk_bytes).finish(row_order)
 
 
 def pack_csr(csr, row_order, gene_idx, n_all_genes, device):
