@@ -198,14 +198,6 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes
 __device__ __forceinline__ uint32_t instr_desc(int M, int N) {
   return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ uint32_t cvt_f16x2(float lo, float hi) {
-  uint32_t r;
-  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
-  return r;
-}
-__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
-  return __half22float2(*reinterpret_cast<const __half2*>(&v));
-}
 // packed f32x2 arithmetic (two cells of one gene per instruction)
 __device__ __forceinline__ unsigned long long pack2(float lo, float hi) {
   return (unsigned long long)__float_as_uint(lo) | ((unsigned long long)__float_as_uint(hi) << 32);
@@ -222,13 +214,31 @@ __device__ __forceinline__ unsigned long long mul2(unsigned long long a, unsigne
   asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
   return d;
 }
-// hi / lo f16 split of a packed pair: hi = f16(v), lo = f16((v - hi) * 2048)
+// f16x2 of a packed f32 pair (low element in the low half)
+__device__ __forceinline__ uint32_t cvt2_f16x2(unsigned long long v) {
+  uint32_t r;
+  asm("{\n.reg .f32 flo, fhi;\nmov.b64 {flo, fhi}, %1;\ncvt.rn.f16x2.f32 %0, fhi, flo;\n}" : "=r"(r) : "l"(v));
+  return r;
+}
+// packed f32 pair of MINUS an f16x2: the sign flip is one XOR on the pair, the two conversions write the
+// halves of the 64-bit result directly (no negations / moves on the f32 side)
+__device__ __forceinline__ unsigned long long neg_unpack2(uint32_t h) {
+  unsigned long long r;
+  asm("{\n.reg .b16 lo, hi;\n.reg .f32 flo, fhi;\nmov.b32 {lo, hi}, %1;\ncvt.f32.f16 flo, lo;\ncvt.f32.f16 fhi, hi;\n"
+      "mov.b64 %0, {flo, fhi};\n}"
+      : "=l"(r)
+      : "r"(h ^ 0x80008000u));
+  return r;
+}
+__device__ __forceinline__ unsigned long long pack2_asm(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+// hi / lo f16 split of a packed pair: hi = f16(v), lo = f16((v - hi) * 2048); (v - hi) is exact in f32
 __device__ __forceinline__ void split2(unsigned long long v, uint32_t& hi, uint32_t& lo) {
-  hi = cvt_f16x2(lo_f(v), hi_f(v));
-  const float2 h = unpack_f16x2(hi);
-  // (v - h) is exact in f32; the negation rides on the f16 -> f32 conversion
-  const unsigned long long r = mul2(add2(v, pack2(-h.x, -h.y)), pack2(kLoScale, kLoScale));
-  lo = cvt_f16x2(lo_f(r), hi_f(r));
+  hi = cvt2_f16x2(v);
+  lo = cvt2_f16x2(mul2(add2(v, neg_unpack2(hi)), pack2(kLoScale, kLoScale)));
 }
 #ifdef __CUDA_FTZ
 #error "g2g_moments_mma.cu must be compiled without -ftz=true / --use_fast_math: nonzero_flag() relies on f32 denormals"
@@ -518,7 +528,7 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
             for (int j = 0; j < ((G2G_MMA_ABLATE & 2) ? 1 : 4); ++j) {
               const float x0 = xs[(8 * half + 2 * j) * kGT], x1 = xs[(8 * half + 2 * j + 1) * kGT];
               nz += nonzero_flag(x0) + nonzero_flag(x1);
-              const unsigned long long x2 = pack2(x0, x1);
+              const unsigned long long x2 = pack2_asm(x0, x1);
               const unsigned long long d2 = add2(x2, neg_a2);
               csum2 = add2(csum2, d2);
               split2(x2, xh[j], xl[j]);
