@@ -557,12 +557,12 @@ class AlignmentEngine:
                                              _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags),
                                              _ptr(self.align_str), _ptr(self.align_len), _ptr(self.opt_cost),
                                              _ptr(self.l_states), st), "g2g_fixup_cost_dp")
-            return 4 if self.sparse else 6  # 2 x (weights[, pilot]) + moments + fused fix-up / DP
+            return 6 if self.sparse else 8  # 2 x (weights + its per-bin sums[, pilot]) + moments + fused fix-up / DP
         _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
                                         _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
                                         _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags), _ptr(self.fix_ws),
                                         self.fix_ws_bytes, st), "g2g_fixup_trends")
-        return 5 if self.sparse else 7  # 2 x (weights[, pilot]) + moments + partial reduce + fix-up
+        return 7 if self.sparse else 9  # 2 x (weights + sums[, pilot]) + moments + partial reduce + fix-up
 
     def run_dp(self, trends=None, cost_in=None, dump=False, gene_slice=None, force_new=False):
         """K4 on all genes (or ``gene_slice`` / the given ``trends``).  ``dump=True`` also returns the

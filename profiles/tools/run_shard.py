@@ -47,5 +47,12 @@ for _ in range(args.reps):
     eng.time_moments(a, b)
     torch.cuda.synchronize()
     k1.append(a.elapsed_time(b))
-print("variant %s step ms %s k1 ms %s -> %.0f GB/s" % (eng.variant, np.round(ms, 3), np.round(k1, 3),
-                                                       4.0 * 2 * n * G / (min(k1) * 1e-3) / 1e9))
+fu = []
+for _ in range(args.reps):
+    flush.fill_(1)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.time_fused(a, b)
+    torch.cuda.synchronize()
+    fu.append(a.elapsed_time(b))
+print("variant %s step ms %s k1 ms %s -> %.0f GB/s; fused ms %s" % (eng.variant, np.round(ms, 3), np.round(k1, 3),
+                                                                    4.0 * 2 * n * G / (min(k1) * 1e-3) / 1e9, np.round(fu, 3)))
