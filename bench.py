@@ -51,6 +51,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--moments", default="auto", choices=["auto", "mma", "ffma"])
     ap.add_argument("--cpu-genes-per-core", type=int, default=2, help="genes per host core in the bounded CPU sample")
+    ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: CTA cap of the NCCL communicator (0 = NCCL's default)")
+    ap.add_argument("--sm-reserve", type=int, default=0,
+                    help="SMs the persistent interpolation kernel leaves free (experiments with overlapped collectives)")
     return ap.parse_args()
 
 
@@ -315,18 +318,18 @@ class DeviceWorkload:
         torch.cuda.synchronize()
 
 
-def capture_graph(eng):
-    """The kernel launches of one pass as a CUDA graph (None when capture is not possible)."""
+def capture_graph(run):
+    """The kernel launches of ``run()`` as a CUDA graph (None when capture is not possible)."""
     import torch
     try:
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
-            eng.run()
+            run()
             side.synchronize()
             with torch.cuda.graph(g, stream=side):
-                eng.run()
+                run()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         return g
@@ -345,7 +348,7 @@ def time_small_workload(name, dropout, dev, steps, warmup):
     eng = w.engine
     eng.run()
     torch.cuda.synchronize()
-    graph = capture_graph(eng)
+    graph = capture_graph(eng.run)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     run = graph.replay if graph is not None else eng.run
     for _ in range(warmup):
@@ -412,7 +415,13 @@ def run_b200(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # the gather's NCCL kernels share the GPU with the next step's kernels: cap their CTAs at the number of SMs
+        # the persistent interpolation kernel leaves free, so that the two really run side by side
+        opts = dist.ProcessGroupNCCL.Options()
+        if args.nccl_max_ctas > 0:
+            opts.config.max_ctas = args.nccl_max_ctas
+            opts.config.min_ctas = 1
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     G, nr, nq, T = shapes(args.workload)
     lo, hi = distributed.shard_range(G, rank, world)
     cap = distributed.max_shard(G, world)
@@ -429,37 +438,64 @@ def run_b200(args):
     w.raw = None
     torch.cuda.empty_cache()
 
+    eng.sm_reserve = args.sm_reserve
     eng.run()   # first run sets kernel attributes / loads modules
     torch.cuda.synchronize()
-    graph = None if args.no_graph else capture_graph(eng)
-    # gather of step k overlaps step k+1: the packed records are copied to a send buffer at the end of the
-    # step (device to device), the collective runs on a side stream and is joined one step later
-    send = torch.empty_like(eng.packed)
-    recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
+    graph = graph_moments = graph_fused = None
+    if not args.no_graph:
+        if world == 1:
+            graph = capture_graph(eng.run)
+        else:   # two graphs: the gather of the previous step is launched between them (see one_step)
+            graph_moments, graph_fused = capture_graph(eng.run_moments), capture_graph(eng.run_fused)
+            graph = graph_moments if (graph_moments is not None and graph_fused is not None) else None
+    # N > 1: the gather of step k-1 runs on a side stream next to step k's fused fix-up / DP launch -- not next to
+    # the interpolation kernel, whose persistent CTAs fill every SM (an NCCL kernel resident first delays the
+    # CTAs of the SMs it holds, and with them the whole statically scheduled pass).  The packed records of a
+    # step are copied to one of two send buffers (device to device), so a step never waits for a gather.
+    send = [torch.empty_like(eng.packed) for _ in range(2)] if world > 1 else None
+    recv = torch.empty((world, eng.packed.numel()), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
     recv_list = list(recv.unbind(0)) if recv is not None else None
     comm_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
-    gather_done = torch.cuda.Event()
-    step_done = torch.cuda.Event()
+    moments_done = torch.cuda.Event()
+    gather_done = [torch.cuda.Event(), torch.cuda.Event()]
+    state = {"k": 0, "pending": None}
+
+    def launch_gather(buf_index):
+        with torch.cuda.stream(comm_stream):
+            dist.gather(send[buf_index], recv_list, dst=0)
+            gather_done[buf_index].record(comm_stream)
 
     def one_step():
-        if graph is not None:
-            graph.replay()
-        else:
-            eng.run()
-        if world > 1:
-            main_stream.wait_event(gather_done)          # the previous gather has read `send`
-            send.copy_(eng.packed)
-            step_done.record(main_stream)
-            comm_stream.wait_event(step_done)
-            with torch.cuda.stream(comm_stream):
-                dist.gather(send, recv_list, dst=0)
-                gather_done.record(comm_stream)
+        if world == 1:
+            graph.replay() if graph is not None else eng.run()
+            return
+        k = state["k"]
+        graph_moments.replay() if graph is not None else eng.run_moments()
+        if state["pending"] is not None:              # records of step k-1: gather them under this step's DP
+            moments_done.record(main_stream)
+            comm_stream.wait_event(moments_done)
+            launch_gather(state["pending"])
+        graph_fused.replay() if graph is not None else eng.run_fused()
+        main_stream.wait_event(gather_done[k & 1])     # the gather that last read this send buffer (step k-2)
+        send[k & 1].copy_(eng.packed)
+        state["pending"] = k & 1
+        state["k"] = k + 1
 
-    gather_done.record(main_stream)
+    def drain():
+        """Gather the records of the last step (nothing is left to overlap them with)."""
+        if world > 1 and state["pending"] is not None:
+            moments_done.record(main_stream)
+            comm_stream.wait_event(moments_done)
+            launch_gather(state["pending"])
+            main_stream.wait_event(gather_done[state["pending"]])
+            state["pending"] = None
+
+    for ev in gather_done:
+        ev.record(main_stream)
     for _ in range(args.warmup):
         one_step()
-    main_stream.wait_event(gather_done)
+    drain()
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -473,7 +509,7 @@ def run_b200(args):
     t_start.record()
     for _ in range(args.steps):
         one_step()
-    main_stream.wait_event(gather_done)   # the last gather belongs to the timed region
+    drain()                               # the last gather belongs to the timed region
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -559,7 +595,8 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_dict(args.workload, args.dropout, world,
                                   {"cuda_graph": graph is not None, "wall_s_timed_region": wall,
-                                   "gather": "overlapped with the next step on a side stream" if world > 1 else "none"}),
+                                   "gather": ("NCCL gather of step k-1 on a side stream next to step k's fused fix-up / DP launch "
+                                              "(two send buffers)") if world > 1 else "none"}),
             "e2e": {"value": G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t * 1e3, "steps": len(e2e_ms),
                     "ms_each": [round(v, 3) for v in e2e_ms],

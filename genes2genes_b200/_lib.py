@@ -53,6 +53,7 @@ SIGNATURES = {
     "g2g_mma_layout": (c_i32, [c_i64, c_i32, ctypes.POINTER(MmaLayout)]),
     "g2g_weights_mma": (c_i32, [c_vp, c_i64, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_moments_mma": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp, c_vp]),
+    "g2g_moments_mma_ex": (c_i32, [ctypes.POINTER(Side), c_i32, c_i64, c_i64, c_i32, c_vp, c_i32, c_vp]),
     "g2g_moments_csc": (c_i32, [ctypes.POINTER(SparseSide), c_i32, c_i64, c_i64, c_i32, c_vp]),
     "g2g_fixup_workspace_bytes": (c_sz, [c_i64, c_i32]),
     "g2g_fixup_trends": (c_i32, [ctypes.POINTER(Side), c_vp, c_vp, c_vp, c_vp, c_vp, c_i64, c_i64, c_i32,

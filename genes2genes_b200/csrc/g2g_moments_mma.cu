@@ -609,7 +609,7 @@ int get_encode_fn(EncodeTiledFn* out) {
 }
 
 template <int N>
-int launch_mma(MmaParams& p, const g2g_side_t* sides, cudaStream_t stream) {
+int launch_mma(MmaParams& p, const g2g_side_t* sides, int sm_reserve, cudaStream_t stream) {
   EncodeTiledFn encode;
   int rc = get_encode_fn(&encode);
   if (rc != G2G_OK) return rc;
@@ -638,7 +638,8 @@ int launch_mma(MmaParams& p, const g2g_side_t* sides, cudaStream_t stream) {
   G2G_CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev));
   const size_t smem = Smem<N>::kTotal;
   G2G_CUDA_TRY(cudaFuncSetAttribute(moments_mma_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int grid = n_sm;   // one CTA per SM: the kernel owns all 512 TMEM columns
+  int grid = n_sm - sm_reserve;   // one CTA per SM: the kernel owns all 512 TMEM columns
+  if (grid < 1) grid = 1;
   if (grid > items) grid = items;
   moments_mma_kernel<N><<<grid, kThreads, smem, stream>>>(p);
   G2G_CUDA_TRY(cudaGetLastError());
@@ -649,6 +650,12 @@ int launch_mma(MmaParams& p, const g2g_side_t* sides, cudaStream_t stream) {
 
 extern "C" int g2g_moments_mma(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
                                int32_t n_bins, int32_t* status, void* stream) {
+  return g2g_moments_mma_ex(sides, n_sides, n_genes, g_stride, n_bins, status, 0, stream);
+}
+
+extern "C" int g2g_moments_mma_ex(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                                  int32_t n_bins, int32_t* status, int32_t sm_reserve, void* stream) {
+  G2G_REQUIRE(sm_reserve >= 0 && sm_reserve < 128, "sm_reserve out of range");
   G2G_REQUIRE(sides != nullptr && n_sides >= 1 && n_sides <= kMaxSides, "n_sides must be 1 or 2");
   G2G_REQUIRE(n_bins >= 2 && n_bins <= G2G_MAX_BINS, "n_bins out of range [2, 128]");
   G2G_REQUIRE(n_genes >= 1 && g_stride >= n_genes, "bad gene counts");
@@ -679,10 +686,10 @@ extern "C" int g2g_moments_mma(const g2g_side_t* sides, int32_t n_sides, int64_t
     G2G_CUDA_TRY(cudaMemsetAsync(in.part_i32, 0, (size_t)lay.n_split * n_bins * g_stride * sizeof(int32_t), st));
   }
   switch (t.n_cols) {
-    case 16: return launch_mma<16>(p, sides, st);
-    case 32: return launch_mma<32>(p, sides, st);
-    case 48: return launch_mma<48>(p, sides, st);
-    case 64: return launch_mma<64>(p, sides, st);
+    case 16: return launch_mma<16>(p, sides, sm_reserve, st);
+    case 32: return launch_mma<32>(p, sides, sm_reserve, st);
+    case 48: return launch_mma<48>(p, sides, sm_reserve, st);
+    case 64: return launch_mma<64>(p, sides, sm_reserve, st);
     default:
       g2g_set_error("n_cols %d has no compiled kernel", t.n_cols);
       return G2G_ERR_UNSUPPORTED;

@@ -476,6 +476,9 @@ class AlignmentEngine:
         self.ref = DeviceSide(X_ref, small["tau_ref"], G, T, small["denom_ref"], dev, self.variant)
         self.query = DeviceSide(X_query, small["tau_query"], G, T, small["denom_query"], dev, self.variant)
         self.k1_status = torch.zeros(2, dtype=torch.int32, device=dev)
+        #: SMs the persistent interpolation kernel leaves free (for a collective of the previous batch that runs
+        #: on another stream while this batch computes; 0 = use every SM)
+        self.sm_reserve = 0
         self.points, self.eps_mean, self.eps_std = small["points"], small["eps_mean"], small["eps_std"]
         self.set_state_params(free_params)
         self.start = start_costs()
@@ -524,9 +527,18 @@ class AlignmentEngine:
         self.trans = transition_costs(self.free_params)
 
     # -- stages -----------------------------------------------------------------------------
+    def run_moments(self):
+        """First half of the hot path: K0 weight tables, K1a pilot means, K1m / K1 weighted moments."""
+        return self.run_interpolation(with_dp=None)
+
+    def run_fused(self):
+        """Second half: the fused fix-up + cost + DP launch on the partial sums of ``run_moments``."""
+        self._launch_fused()
+
     def run_interpolation(self, with_dp=False):
         """K0 / pilot / K1 and the per-gene fix-up.  ``with_dp=True`` finishes with the fused fix-up +
-        cost + DP launch (``g2g_fixup_cost_dp``) instead of ``g2g_fixup_trends``: the whole hot path."""
+        cost + DP launch (``g2g_fixup_cost_dp``) instead of ``g2g_fixup_trends``: the whole hot path
+        (``with_dp=None``: stop after the moments)."""
         lib, T, G = self.lib, self.n_bins, self.n_genes
         cur = torch.cuda.current_stream()
         # four independent small kernels: the weight tables of the two datasets go to two forked streams,
@@ -548,6 +560,8 @@ class AlignmentEngine:
         cur.wait_event(self._ev_join2)
         st = _stream()
         self._launch_moments(st)
+        if with_dp is None:
+            return 5 if self.sparse else 7
         if with_dp:
             trans_c = (c_f64 * 25)(*np.asarray(self.trans, dtype=np.float64).reshape(-1).tolist())
             start_c = (c_f64 * 3)(*np.asarray(self.start, dtype=np.float64).tolist())
@@ -582,7 +596,8 @@ class AlignmentEngine:
         if self.variant == "csc":
             _lib.check(lib.g2g_moments_csc(self._sparse_sides, 2, G, G, T, st), "g2g_moments_csc")
         elif self.variant == "mma":
-            _lib.check(lib.g2g_moments_mma(self._sides, 2, G, G, T, _ptr(self.k1_status), st), "g2g_moments_mma")
+            _lib.check(lib.g2g_moments_mma_ex(self._sides, 2, G, G, T, _ptr(self.k1_status), int(self.sm_reserve), st),
+                       "g2g_moments_mma")
         else:
             _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
 
@@ -596,17 +611,20 @@ class AlignmentEngine:
     def time_fused(self, start_event, end_event):
         """Launch the fused fix-up + cost + DP kernel alone between two CUDA events (its inputs are the partial
         sums of the last run)."""
+        start_event.record()
+        self._launch_fused()
+        end_event.record()
+
+    def _launch_fused(self):
         T, G = self.n_bins, self.n_genes
         trans_c = (c_f64 * 25)(*np.asarray(self.trans, dtype=np.float64).reshape(-1).tolist())
         start_c = (c_f64 * 3)(*np.asarray(self.start, dtype=np.float64).tolist())
-        start_event.record()
         _lib.check(self.lib.g2g_fixup_cost_dp(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w),
                                               _ptr(self.points), _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T,
                                               trans_c, start_c, float(self.c_model), N_SAMPLES, _ptr(self.musigma),
                                               _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags),
                                               _ptr(self.align_str), _ptr(self.align_len), _ptr(self.opt_cost),
                                               _ptr(self.l_states), _stream()), "g2g_fixup_cost_dp")
-        end_event.record()
 
     def run(self, fused=True):
         """The whole hot path on the current stream.  ``fused=False`` runs the fix-up and the DP as the

@@ -198,6 +198,11 @@ int g2g_weights_mma(const double* tau, int64_t n_cells, const double* points, co
                     void* stream);
 int g2g_moments_mma(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
                     int32_t n_bins, int32_t* status, void* stream);
+/* The same with `sm_reserve` SMs left without a CTA of the (persistent, one CTA per SM) kernel: a collective of
+ * the previous batch running on another stream (the NCCL gather of the result records, whose kernels need a
+ * few SMs) can then overlap this pass instead of waiting for it.  Results do not depend on the grid size. */
+int g2g_moments_mma_ex(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64_t g_stride,
+                       int32_t n_bins, int32_t* status, int32_t sm_reserve, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1s g2g_moments_csc -- sparse variant of g2g_moments: the expression matrix
