@@ -353,7 +353,8 @@ class _LazyPairs(dict):
 
     def __init__(self, store):
         super().__init__()
-        self._store = store
+        import weakref
+        self._store = weakref.proxy(store)   # no reference cycle: a dropped aligner frees its staging buffer at once
 
     def __missing__(self, gene):
         st = self._store.series_pair(self._store.gene_index[gene])
@@ -655,6 +656,10 @@ class RefQueryAligner:
                     on_enqueued()
                 host = eng.finish_results_to_host()
             else:
+                if on_enqueued is not None:
+                    on_enqueued()
+                if eng is not None:
+                    eng.redo_if_out_of_range()
                 host = self._gather_results()
         if store is None:
             store = self._new_store(host)
@@ -699,8 +704,13 @@ class RefQueryAligner:
         dist.gather(send, list(recv.unbind(0)) if rank == 0 else None, dst=0)
         if rank != 0:
             if eng is None:
-                return _engine.unpack_results(np.zeros(send.numel(), dtype=np.uint8), cap, T, 0)
+                empty = np.zeros(max(n_bytes, 8), dtype=np.uint8)
+                return _engine.HostResults([(empty, cap, 0, 0)], 0, T)
             return eng.results_to_host()
+        segments = []
+        for r in range(world):
+            lo, hi = D.shard_range(n_all, r, world)
+            segments.append((None, cap, hi - lo, lo))
         host_buf = None
         if on_host:
             raw = recv.numpy()
@@ -709,20 +719,12 @@ class RefQueryAligner:
             host_buf.copy_(recv.view(-1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             raw = host_buf.numpy().reshape(world, -1)
-        # one pass from the (pinned) receive buffer into per-key arrays that cover every gene
-        shapes = _engine.result_shapes(n_all, T)
-        out = {k: np.empty(shapes[k][0], dtype=_engine._NP_DTYPES[shapes[k][1]]) for k in _engine.AlignmentEngine.RESULT_KEYS}
-        for r in range(world):
-            lo, hi = D.shard_range(n_all, r, world)
-            if hi > lo:
-                part = _engine.unpack_results(raw[r], cap, T, hi - lo)
-                for k, v in part.items():
-                    out[k][lo:hi] = v
-        if host_buf is not None:
-            _engine._give_pinned(host_buf)
+        segments = [(raw[r], c, held, lo) for r, (_, c, held, lo) in enumerate(segments)]
         self.gene_list = self._all_genes                    # rank 0 now holds every gene's result
         self._shard = (0, n_all)
-        return out
+        # per-key arrays covering every gene, filled straight from the (pinned) receive buffer: the small ones now,
+        # the large ones on first access
+        return _engine.HostResults(segments, n_all, T, pinned=host_buf)
 
     def _make_result(self, idx, host=None):
         return AligmentObj(self._store, idx, self.gene_list[idx], host)
@@ -749,9 +751,19 @@ class RefQueryAligner:
         self._say("Running gene-level alignment: \U0001F9EC")
         by_gene = None
         if self._dist is not None:
-            self._run_batch()                                   # rank 0's gene_list grows to all genes here
-            store = self._store
-            self.results = [AligmentObj(store, k, g) for k, g in enumerate(self.gene_list)]
+            # rank 0 serves every gene after the gather: its result views are built while the GPUs work
+            genes = self._all_genes if self._dist[0] == 0 else self.gene_list
+            store = _ResultStore(None, genes, self.n_artificial_time_points,
+                                 _engine.epsilon_table(self.n_artificial_time_points),
+                                 self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
+                                 self.state_params, self.device)
+            built, by_gene = [], {}
+
+            def build_views():
+                built.extend(AligmentObj(store, k, g) for k, g in enumerate(genes))
+                by_gene.update((a.gene, a) for a in built)
+            self._run_batch(on_enqueued=build_views, store=store)   # rank 0's gene_list grows to all genes here
+            self.results = built
         else:
             # the result objects are O(1) views: build them while the GPU is still working
             store = self._new_store(None)

@@ -433,6 +433,79 @@ def unpack_results(raw, n_rows, n_bins, n_valid=None):
     return host
 
 
+class HostResults:
+    """name -> numpy array: the per-gene result arrays of a batch on the host (dict-like, read-only).
+
+    The device->host copy lands in a pinned staging buffer.  The small arrays every result object needs
+    (optimal costs, lengths, flags, counts, alignment strings) are copied out of it at once; the large ones
+    (trends, interpolated means / stds, landscape states: 97 % of the bytes) move to their own arrays on first
+    access, and the staging buffer goes back to the pool when the last of them has moved or this object dies.
+    ``segments`` = [(raw u8 view laid out for ``capacity`` genes, capacity, genes held, first gene index)]:
+    one for a single GPU, one per rank after a gather."""
+
+    EAGER = ("opt_cost", "align_len", "flags", "nnz", "align_str")
+
+    def __init__(self, segments, n_genes, n_bins, pinned=None):
+        self._segments, self._n, self._T, self._pinned = segments, int(n_genes), int(n_bins), pinned
+        self._arrays = {}
+        self._shapes = result_shapes(self._n, self._T)
+        self._views = [(unpack_results(raw, cap, self._T, held), lo, held) for raw, cap, held, lo in segments]
+        for k in self.EAGER:
+            self._materialize(k)
+
+    def _materialize(self, key):
+        shape, dt = self._shapes[key]
+        out = np.empty(shape, dtype=_NP_DTYPES[dt])
+        for views, lo, held in self._views:
+            if held:
+                out[lo:lo + held] = views[key]
+        self._arrays[key] = out
+        if len(self._arrays) == len(AlignmentEngine.RESULT_KEYS):
+            self._release()
+        return out
+
+    def _release(self):
+        self._views = self._segments = None
+        if self._pinned is not None:
+            _give_pinned(self._pinned)
+            self._pinned = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def __getitem__(self, key):
+        arr = self._arrays.get(key)
+        if arr is None:
+            if key not in self._shapes:
+                raise KeyError(key)
+            arr = self._materialize(key)
+        return arr
+
+    def __contains__(self, key):
+        return key in self._shapes
+
+    def __iter__(self):
+        return iter(AlignmentEngine.RESULT_KEYS)
+
+    def __len__(self):
+        return len(AlignmentEngine.RESULT_KEYS)
+
+    def keys(self):
+        return list(AlignmentEngine.RESULT_KEYS)
+
+    def values(self):
+        return [self[k] for k in AlignmentEngine.RESULT_KEYS]
+
+    def items(self):
+        return [(k, self[k]) for k in AlignmentEngine.RESULT_KEYS]
+
+    def get(self, key, default=None):
+        return self[key] if key in self._shapes else default
+
+
 class AlignmentEngine:
     """Runs the whole hot path for one (reference, query) pair of packed device matrices.
 
@@ -655,9 +728,24 @@ class AlignmentEngine:
             self._status_host.copy_(self.k1_status.view(torch.uint8), non_blocking=True)
         self._pending_parts = [getattr(self, k) for k in self.RESULT_KEYS]
 
+    def redo_if_out_of_range(self):
+        """Tensor-core kernel only: read its status word (one small synchronous copy) and, if a value did not
+        fit the f16 split (|x| >= 65504 or |x - pilot| >= 255) or the input is not finite, redo the batch with
+        the f32 kernel, which has no range limit.  Returns True when it did.  (The single-GPU result copy
+        checks the status word as part of ``finish_results_to_host``; the multi-GPU path calls this before
+        the gather.)"""
+        if self.variant != "mma":
+            return False
+        if not int(self.k1_status[0].item()) & 1:
+            return False
+        self.k1_status.zero_()
+        self.use_variant("ffma")
+        self.run_interpolation(with_dp=True)
+        return True
+
     def finish_results_to_host(self):
-        """Wait for the copy started by ``begin_results_to_host``; returns name -> numpy array (views of
-        one private host copy of the staging buffer, which goes back to the pool)."""
+        """Wait for the copy started by ``begin_results_to_host``; returns a ``HostResults`` (name -> numpy
+        array) over the private pinned staging buffer."""
         torch.cuda.current_stream().synchronize()
         if self.variant == "mma":
             status = int(self._status_host.numpy().view(np.int32)[0])
@@ -673,10 +761,8 @@ class AlignmentEngine:
                 self.begin_results_to_host()
                 return self.finish_results_to_host()
         self._pending_parts = None
-        raw = self._host_buf.numpy().copy()
-        _give_pinned(self._host_buf)
-        self._host_buf = None
-        return unpack_results(raw, self.capacity, self.n_bins, self.n_genes)
+        buf, self._host_buf = self._host_buf, None
+        return HostResults([(buf.numpy(), self.capacity, self.n_genes, 0)], self.n_genes, self.n_bins, pinned=buf)
 
 
 _PINNED = {}      # n_bytes -> [pinned buffer, event of the last copy that read or wrote it]  (upload staging)
