@@ -85,10 +85,12 @@ __device__ __forceinline__ Item decode_item(const MmaParams& p, int item) {
   it.side = (p.n_sides > 1 && item >= p.side[1].item_base) ? 1 : 0;
   const MmaSide& s = p.side[it.side];
   int r = item - s.item_base;
+  // the bin group varies fastest: the (at most two) passes over an X tile of a T > 64 run are made by
+  // neighbouring CTAs at the same time, so the second read of the tile is served by L2, not by HBM
+  it.bg = r % p.n_groups;
+  r /= p.n_groups;
   it.gt = r % p.n_gtiles;
-  r /= p.n_gtiles;
-  it.split = r % s.n_split;
-  it.bg = r / s.n_split;
+  it.split = r / p.n_gtiles;
   it.row0 = (long long)it.split * s.cells_per_item;
   long long rows = s.n_pad - it.row0;
   if (rows > s.cells_per_item) rows = s.cells_per_item;
