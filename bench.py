@@ -590,7 +590,7 @@ def run_b200(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None,
-            "dtype": ("f16 hi/lo split operands, f32 tensor-core chains of 256 cells, f32/f64 accumulation (interpolation); "
+            "dtype": ("f16 hi/lo split operands, f32 tensor-core chains of 128 cells, f32/f64 accumulation (interpolation); "
                       "f64 (cost + DP)") if mma else "f32 products / f64 accumulation (interpolation), f64 (cost + DP)",
             "data": "synthetic",
             "config": config_dict(args.workload, args.dropout, world),     # identical in the reference arm

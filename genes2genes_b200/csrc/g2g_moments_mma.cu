@@ -15,7 +15,7 @@
 //   * one thread issues six MMAs per K step:  hhA += xh.wh, hhB += yh.wh, loA += xl.wh + xh.wl,
 //     loB += yl.wh + yh.wl  (f32 accumulators in TMEM; the lo.lo product, 2^-22 of the result, is dropped);
 //   * the tensor core truncates when it adds (profiles/r02_umma_ts_probe.txt: -1e-7 of the sum per step),
-//     so the hh chains are cut every kFlushSteps = 16 steps (256 cells): flusher warps read the accumulator
+//     so the hh chains are cut every kFlushSteps = 8 steps (128 cells): flusher warps read the accumulator
 //     (two buffers alternate) and add it, round to nearest, to f32 registers; at the end of a work item they
 //     add the lo accumulator / 2048 in f64 and write the item's partial sums.
 //
@@ -34,7 +34,9 @@ constexpr int kGT = 128;               // genes per tile = TMEM lanes
 constexpr int kStageCells = G2G_CELL_TILE;
 constexpr int kStepCells = 16;         // K of one kind::f16 MMA
 constexpr int kStepsPerStage = kStageCells / kStepCells;
-constexpr int kFlushSteps = 16;        // K steps per first-level accumulation chain
+constexpr int kFlushSteps = 8;         // K steps per first-level accumulation chain.  Measured on a C4 block, max error of the
+                                       // means / stds vs the f64 oracle: 16 steps 0.585 ms / 2.9e-6, 8 steps 0.595 ms / 1.0e-6
+                                       // (the f32 FFMA2 kernel: 1.1e-6), 4 steps 0.611 ms / 3.8e-7
 constexpr int kStages = 4;
 constexpr int kABufs = 4;              // A operand staging buffers in TMEM (32 columns each)
 constexpr int kConvGroups = 4;         // converter groups of 4 warps (one warp per 32 TMEM lanes); the pipeline is
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
   uint64_t* stage_empty = stage_full + kStages;      // [kStages]  MMAs of the stage's 4 steps done
   uint64_t* a_full = stage_empty + kStages;          // [kABufs]   converters wrote the A operands (4 warps)
   uint64_t* a_empty = a_full + kABufs;               // [kABufs]   MMAs that read them done
-  uint64_t* acc_full = a_empty + kABufs;             // [2]        a 256-cell chain is complete
+  uint64_t* acc_full = a_empty + kABufs;             // [2]        a 128-cell chain is complete
   uint64_t* acc_empty = acc_full + 2;                // [2]        flushers have read it (kFlushWarps)
   uint64_t* lo_full = acc_empty + 2;                 // [1]        item complete
   uint64_t* lo_empty = lo_full + 1;                  // [1]

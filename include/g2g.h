@@ -170,7 +170,7 @@ int g2g_moments(const g2g_side_t* sides, int32_t n_sides, int64_t n_genes, int64
  * way by g2g_weights_mma into a shared-memory B operand table, and three products per moment are kept
  * (hi.hi, lo.hi + hi.lo: 22 bits of each factor); sum (x - a) is added up on the CUDA cores.  The tensor core truncates when it accumulates
  * (measured -1e-7 of the sum per 16-cell step, profiles/r02_umma_ts_probe.txt), so the hi.hi chains are
- * cut every 256 cells: the accumulators are read back and added in f32 round-to-nearest registers, which
+ * cut every 128 cells: the accumulators are read back and added in f32 round-to-nearest registers, which
  * are added in f64 once per work item.  Values with |x| >= 65504 or |x - a| >= 255 do not fit the f16
  * split: the kernel then sets bit 0 of *status and the caller must redo the batch with g2g_moments.
  *   sides[s].wtab = the table of g2g_weights_mma; part_f64 / part_i32 as for g2g_moments but with
