@@ -44,6 +44,8 @@ SIGNATURES = {
     "g2g_layout": (c_i32, [c_i64, c_i32, ctypes.POINTER(Layout)]),
     "g2g_pack_rows": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_pack_csr": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
+    "g2g_csr_to_csc_workspace_bytes": (c_sz, [c_i64, c_i64]),
+    "g2g_csr_to_csc": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
     "g2g_upload_block": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "g2g_scatter_rows": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_weights_workspace_bytes": (c_sz, [c_i64, c_i32]),

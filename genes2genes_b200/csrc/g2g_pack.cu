@@ -45,7 +45,131 @@ __global__ void __launch_bounds__(256) pack_csr_kernel(const long long* __restri
   }
 }
 
+// ---- CSR (cells x all genes) -> CSC of the selected genes with time-sorted, ascending row indices ----
+// A stable counting sort by column, deterministic without a general sort: the time-sorted rows are cut
+// into chunks of kChunkRows; (1) every chunk counts its entries per selected column, (2) a per-column
+// exclusive scan over the chunks turns the counts into each chunk's first position inside the column,
+// (3) a scan over the columns gives col_ptr, (4) every chunk walks its rows IN ORDER (one block per chunk,
+// a block barrier between rows) and appends each entry at its column's running position -- columns are
+// unique inside a CSR row, so the running positions need no atomics.
+constexpr int kChunkRows = 1024;
+constexpr int kCscThreads = 256;
+
+struct CscParams {
+  const long long* indptr;
+  const int* indices;
+  const float* data;
+  const long long* row_order;   // CSR row of the k-th cell in time order (null: identity)
+  const int* col_map;           // source column -> selected gene (-1: dropped; null: identity)
+  long long n_cells;
+  int n_genes, n_chunks;
+  int* chunk_pos;               // [n_chunks][n_genes]: counts, then first positions
+  long long* col_ptr;           // [n_genes + 1]
+  int* row_idx;
+  float* values;
+};
+
+__global__ void __launch_bounds__(kCscThreads) csc_count_kernel(const CscParams p) {
+  const int chunk = blockIdx.x;
+  int* cnt = p.chunk_pos + (size_t)chunk * p.n_genes;
+  const long long r0 = (long long)chunk * kChunkRows;
+  const long long r1 = r0 + kChunkRows < p.n_cells ? r0 + kChunkRows : p.n_cells;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long long r = r0 + warp; r < r1; r += kCscThreads / 32) {
+    const long long sr = p.row_order ? p.row_order[r] : r;
+    const long long b = p.indptr[sr], e = p.indptr[sr + 1];
+    for (long long k = b + lane; k < e; k += 32) {
+      int c = p.indices[k];
+      if (p.col_map) c = p.col_map[c];
+      if (c >= 0) atomicAdd(&cnt[c], 1);
+    }
+  }
+}
+
+// per column: exclusive scan of the chunk counts (in place) and the column total
+__global__ void __launch_bounds__(256) csc_chunk_scan_kernel(const CscParams p, long long* col_count) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= p.n_genes) return;
+  int run = 0;
+  for (int k = 0; k < p.n_chunks; ++k) {
+    int* slot = p.chunk_pos + (size_t)k * p.n_genes + c;
+    const int v = *slot;
+    *slot = run;
+    run += v;
+  }
+  col_count[c] = run;
+}
+
+// col_ptr = exclusive scan of the column totals (one block; counts sit in col_ptr[1..] on entry)
+__global__ void __launch_bounds__(1024) csc_col_scan_kernel(long long* col_ptr, int n_genes) {
+  __shared__ long long s_part[1024];
+  const int tid = threadIdx.x;
+  const int per = (n_genes + 1023) / 1024;
+  const int lo = tid * per, hi = min(n_genes, lo + per);
+  long long sum = 0;
+  for (int c = lo; c < hi; ++c) sum += col_ptr[1 + c];
+  s_part[tid] = sum;
+  __syncthreads();
+  if (tid == 0) {
+    long long run = 0;
+    for (int k = 0; k < 1024; ++k) { const long long v = s_part[k]; s_part[k] = run; run += v; }
+    col_ptr[0] = 0;
+  }
+  __syncthreads();
+  long long run = s_part[tid];
+  for (int c = lo; c < hi; ++c) { run += col_ptr[1 + c]; col_ptr[1 + c] = run; }   // inclusive sums = col_ptr[c + 1]
+}
+
+__global__ void __launch_bounds__(kCscThreads) csc_fill_kernel(const CscParams p) {
+  const int chunk = blockIdx.x;
+  int* pos = p.chunk_pos + (size_t)chunk * p.n_genes;
+  const long long r0 = (long long)chunk * kChunkRows;
+  const long long r1 = r0 + kChunkRows < p.n_cells ? r0 + kChunkRows : p.n_cells;
+  for (long long r = r0; r < r1; ++r) {     // rows strictly in time order
+    const long long sr = p.row_order ? p.row_order[r] : r;
+    const long long b = p.indptr[sr], e = p.indptr[sr + 1];
+    for (long long k = b + threadIdx.x; k < e; k += kCscThreads) {
+      int c = p.indices[k];
+      if (p.col_map) c = p.col_map[c];
+      if (c >= 0) {
+        const long long at = p.col_ptr[c] + pos[c];
+        pos[c] += 1;                        // one entry per (row, column): no other thread touches pos[c] in this row
+        p.row_idx[at] = (int)r;
+        p.values[at] = p.data[k];
+      }
+    }
+    __syncthreads();                        // the next row sees this row's positions
+  }
+}
+
 }  // namespace
+
+extern "C" size_t g2g_csr_to_csc_workspace_bytes(int64_t n_cells, int64_t n_genes) {
+  const int64_t n_chunks = g2g_ceil_div(n_cells, kChunkRows);
+  return (size_t)n_chunks * (size_t)n_genes * sizeof(int);
+}
+
+extern "C" int g2g_csr_to_csc(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_cells,
+                              const int64_t* row_order, const int32_t* col_map, int64_t n_genes, int64_t* col_ptr,
+                              int32_t* row_idx, float* values, void* workspace, size_t workspace_bytes, void* stream) {
+  G2G_REQUIRE(indptr && indices && data && col_ptr && row_idx && values && workspace, "null pointer");
+  G2G_REQUIRE(n_cells >= 1 && n_cells < (1ll << 31) && n_genes >= 1 && n_genes < (1ll << 31), "bad shape");
+  G2G_REQUIRE(workspace_bytes >= g2g_csr_to_csc_workspace_bytes(n_cells, n_genes), "workspace too small");
+  cudaStream_t st = (cudaStream_t)stream;
+  CscParams p;
+  p.indptr = reinterpret_cast<const long long*>(indptr); p.indices = indices; p.data = data;
+  p.row_order = reinterpret_cast<const long long*>(row_order); p.col_map = col_map;
+  p.n_cells = n_cells; p.n_genes = (int)n_genes; p.n_chunks = (int)g2g_ceil_div(n_cells, kChunkRows);
+  p.chunk_pos = reinterpret_cast<int*>(workspace);
+  p.col_ptr = reinterpret_cast<long long*>(col_ptr); p.row_idx = row_idx; p.values = values;
+  G2G_CUDA_TRY(cudaMemsetAsync(workspace, 0, g2g_csr_to_csc_workspace_bytes(n_cells, n_genes), st));
+  csc_count_kernel<<<p.n_chunks, kCscThreads, 0, st>>>(p);
+  csc_chunk_scan_kernel<<<(unsigned)g2g_ceil_div(n_genes, 256), 256, 0, st>>>(p, p.col_ptr + 1);
+  csc_col_scan_kernel<<<1, 1024, 0, st>>>(p.col_ptr, p.n_genes);
+  csc_fill_kernel<<<p.n_chunks, kCscThreads, 0, st>>>(p);
+  G2G_CUDA_TRY(cudaGetLastError());
+  return G2G_OK;
+}
 
 extern "C" int g2g_pack_rows(const float* src, int64_t n_cells, int64_t n_genes, int64_t ld_src,
                              const int64_t* row_order, const int32_t* gene_idx, float* dst, int64_t ld_dst,

@@ -384,30 +384,33 @@ def run_cost_dp(trends, n_bins, trans, start, c_model, cost_in=None, dump=False,
 
 
 def pack_csc(csr, row_order, gene_idx, n_all_genes, device):
-    """scipy CSR (cells x all genes) -> time-sorted, gene-selected ``CscMatrix`` on the device.  Only the
-    stored entries cross PCIe; the transposition is a stable device sort by (gene, sorted cell)."""
-    n_cells = csr.shape[0]
-    n_genes = n_all_genes if gene_idx is None else len(gene_idx)
+    """scipy CSR (cells x all genes, canonical: no duplicate entries) -> time-sorted, gene-selected
+    ``CscMatrix`` on the device.  Only the stored entries cross PCIe; the transposition is
+    ``g2g_csr_to_csc`` (a stable counting sort by column: rows stay in time order inside every column)."""
+    lib = _lib.load()
+    n_cells = int(csr.shape[0])
+    n_genes = int(n_all_genes if gene_idx is None else len(gene_idx))
     indptr = torch.from_numpy(np.ascontiguousarray(csr.indptr, dtype=np.int64)).to(device, non_blocking=True)
-    cols = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int64)).to(device, non_blocking=True)
+    cols = torch.from_numpy(np.ascontiguousarray(csr.indices, dtype=np.int32)).to(device, non_blocking=True)
     vals = torch.from_numpy(np.ascontiguousarray(csr.data, dtype=np.float32)).to(device, non_blocking=True)
-    rows = torch.repeat_interleave(torch.arange(n_cells, device=device), indptr[1:] - indptr[:-1])
-    if row_order is not None:  # rank of every original row in the time-sorted order
-        rank = torch.empty(n_cells, dtype=torch.int64, device=device)
-        rank[torch.as_tensor(np.ascontiguousarray(row_order, dtype=np.int64)).to(device)] = torch.arange(
-            n_cells, device=device)
-        rows = rank[rows]
+    ro = cm = None
+    if row_order is not None:
+        ro = torch.from_numpy(np.ascontiguousarray(row_order, dtype=np.int64)).to(device, non_blocking=True)
     if gene_idx is not None:
-        cm = np.full(n_all_genes, -1, dtype=np.int64)
-        cm[np.asarray(gene_idx)] = np.arange(n_genes)
-        cols = torch.from_numpy(cm).to(device)[cols]
-        keep = cols >= 0
-        cols, rows, vals = cols[keep], rows[keep], vals[keep]
-    key, perm = torch.sort(cols * n_cells + rows)  # keys are unique: (gene, cell) pairs
-    counts = torch.bincount(cols, minlength=n_genes)
-    col_ptr = torch.zeros(n_genes + 1, dtype=torch.int64, device=device)
-    torch.cumsum(counts, 0, out=col_ptr[1:])
-    return CscMatrix(col_ptr, (key % n_cells).to(torch.int32), vals[perm].contiguous(), n_cells, n_genes)
+        cm_h = np.full(n_all_genes, -1, dtype=np.int32)
+        cm_h[np.asarray(gene_idx)] = np.arange(n_genes, dtype=np.int32)
+        cm = torch.from_numpy(cm_h).to(device, non_blocking=True)
+    nnz = int(vals.numel())
+    col_ptr = torch.empty(n_genes + 1, dtype=torch.int64, device=device)
+    row_idx = torch.empty(max(nnz, 1), dtype=torch.int32, device=device)
+    values = torch.empty(max(nnz, 1), dtype=torch.float32, device=device)
+    ws_bytes = lib.g2g_csr_to_csc_workspace_bytes(n_cells, n_genes)
+    ws = torch.empty(max((ws_bytes + 3) // 4, 1), dtype=torch.int32, device=device)
+    _lib.check(lib.g2g_csr_to_csc(_ptr(indptr), _ptr(cols), _ptr(vals), n_cells, _ptr(ro), _ptr(cm), n_genes,
+                                  _ptr(col_ptr), _ptr(row_idx), _ptr(values), _ptr(ws), ws_bytes, _stream()),
+               "g2g_csr_to_csc")
+    kept = nnz if gene_idx is None else int(col_ptr[-1].item())    # entries of the selected genes
+    return CscMatrix(col_ptr, row_idx[:kept], values[:kept], n_cells, n_genes)
 
 
 def result_shapes(n_rows, n_bins):

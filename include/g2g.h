@@ -83,6 +83,17 @@ int g2g_pack_csr(const int64_t* indptr, const int32_t* indices, const float* dat
                  const int64_t* row_order, const int32_t* col_map, float* dst, int64_t ld_dst,
                  void* stream);
 
+/* g2g_csr_to_csc -- the sparse twin of the same step: a CSR matrix (cells x all genes, entries unique per
+ * (row, column)) becomes the gene-major CSC matrix g2g_moments_csc streams: selected genes only
+ * (col_map[c] = gene or -1; null = identity), cells in time order (row_order[k] = CSR row of the k-th cell;
+ * null = identity), row indices ascending inside every column.  A stable counting sort by column (per
+ * 1024-row chunk counts, scans, ordered fill): deterministic, no general sort.  col_ptr i64 [n_genes+1];
+ * row_idx / values need room for every stored entry of the input; workspace as reported, 4-byte aligned. */
+size_t g2g_csr_to_csc_workspace_bytes(int64_t n_cells, int64_t n_genes);
+int g2g_csr_to_csc(const int64_t* indptr, const int32_t* indices, const float* data, int64_t n_cells,
+                   const int64_t* row_order, const int32_t* col_map, int64_t n_genes, int64_t* col_ptr,
+                   int32_t* row_idx, float* values, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * g2g_upload_block / g2g_scatter_rows -- the host->device leg of the same step, for a HOST matrix
  * (`adata.X`, row major f32, cells x all genes), pipelined by row chunk: only the column block
