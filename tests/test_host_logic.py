@@ -347,3 +347,38 @@ def test_bench_reference_arm_prints_one_contract_line():
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["sequential_value"] > 0 and d["scaling"] == "strong"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_host_results_assemble_rank_segments_lazily():
+    """`engine.HostResults`: per-rank packed records laid out for the largest shard (capacity) become arrays
+    covering every gene; the small arrays are copied at once, the large ones on first access, and the staging
+    views are dropped when the last one has moved (the gather path of `RefQueryAligner(distributed=True)`)."""
+    import torch
+    from genes2genes_b200 import distributed as D
+    n_all, world, T = 11, 4, 6
+    cap = D.max_shard(n_all, world)
+    rng = np.random.default_rng(0)
+    want = {k: None for k in engine.AlignmentEngine.RESULT_KEYS}
+    shapes = engine.result_shapes(n_all, T)
+    np_dt = {torch.float64: np.float64, torch.int32: np.int32, torch.uint8: np.uint8}
+    for k, (shape, dt) in shapes.items():
+        want[k] = (rng.uniform(0, 200, size=shape)).astype(np_dt[dt])
+    segments = []
+    for r in range(world):
+        lo, hi = D.shard_range(n_all, r, world)
+        raw = np.zeros(D.record_bytes(cap, T), dtype=np.uint8)
+        views = engine.unpack_results(raw, cap, T)
+        for k in views:
+            views[k][: hi - lo] = want[k][lo:hi]
+        segments.append((raw, cap, hi - lo, lo))
+    host = engine.HostResults(segments, n_all, T)
+    assert set(host._arrays) == set(engine.HostResults.EAGER) and host._views is not None
+    assert "trends" in host and "nope" not in host
+    with pytest.raises(KeyError):
+        host["nope"]
+    for k in engine.AlignmentEngine.RESULT_KEYS:
+        assert np.array_equal(host[k], want[k]), k
+    assert host._views is None and host._segments is None      # staging released after the last array moved
+    for raw, *_ in segments:                                    # the arrays own their memory
+        raw[:] = 0
+    assert np.array_equal(host["musigma"], want["musigma"])
