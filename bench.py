@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--moments", default="auto", choices=["auto", "mma", "ffma"])
     ap.add_argument("--cpu-genes-per-core", type=int, default=2, help="genes per host core in the bounded CPU sample")
+    ap.add_argument("--gather", choices=("peer", "nccl"), default="peer",
+                    help="N > 1: how the result records reach rank 0 (peer: copies into rank 0's window; nccl: dist.gather)")
     ap.add_argument("--nccl-max-ctas", type=int, default=0, help="N > 1: CTA cap of the NCCL communicator (0 = NCCL's default)")
     ap.add_argument("--sm-reserve", type=int, default=0,
                     help="SMs the persistent interpolation kernel leaves free (experiments with overlapped collectives)")
@@ -68,7 +70,7 @@ def config_dict(name, dropout, n_gpus, extra=None):
                        "synthetic log1p counts, dropout parameter %.2f" % (name, G, nr, nq, T, dropout),
            "n_genes": G, "genes_per_gpu": -(-G // n_gpus), "n_ref_cells": nr, "n_query_cells": nq,
            "n_interpolation_points": T,
-           "parallelism": ("genes sharded over %d GPUs in contiguous blocks, one NCCL gather of the result records "
+           "parallelism": ("genes sharded over %d GPUs in contiguous blocks, one gather of the result records "
                            "to rank 0 per step" % n_gpus) if n_gpus > 1 else "single GPU",
            "l2": "inputs larger than L2 (%.1f GB of expression values per rank per step); no flush"
                  % (4.0 * (nr + nq) * (-(-G // n_gpus)) / 1e9)}
@@ -448,16 +450,26 @@ def run_b200(args):
         else:   # two graphs: the gather of the previous step is launched between them (see one_step)
             graph_moments, graph_fused = capture_graph(eng.run_moments), capture_graph(eng.run_fused)
             graph = graph_moments if (graph_moments is not None and graph_fused is not None) else None
-    # N > 1: the gather of step k-1 runs on a side stream next to step k's fused fix-up / DP launch -- not next to
-    # the interpolation kernel, whose persistent CTAs fill every SM (an NCCL kernel resident first delays the
-    # CTAs of the SMs it holds, and with them the whole statically scheduled pass).  The packed records of a
-    # step are copied to one of two send buffers (device to device), so a step never waits for a gather.
-    send = [torch.empty_like(eng.packed) for _ in range(2)] if world > 1 else None
-    recv = torch.empty((world, eng.packed.numel()), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
-    recv_list = list(recv.unbind(0)) if recv is not None else None
+    # N > 1, the gather.  Default: every rank copies its packed records into rank 0's peer-mapped window with one
+    # device-to-device copy over NVLink on a side stream (a copy engine, no kernel), under the next step's kernels.
+    # --gather nccl (or a box that cannot map the window): the NCCL gather of step k-1 runs on a side stream next to
+    # step k's fused fix-up / DP launch -- not next to the interpolation kernel, whose persistent CTAs fill every SM
+    # (an NCCL kernel resident first delays the CTAs of the SMs it holds, and with them the whole statically
+    # scheduled pass); the records of a step are first copied to one of two send buffers.
+    window = None
+    if world > 1 and args.gather == "peer":
+        window = distributed.peer_window(eng.packed.numel(), dev)
+    use_nccl = world > 1 and window is None
+    send = [torch.empty_like(eng.packed) for _ in range(2)] if use_nccl else None
+    recv = torch.empty((world, eng.packed.numel()), dtype=torch.uint8, device=dev) if (use_nccl and rank == 0) else None
+    if window is not None and rank == 0:
+        recv = window.rows()
+    recv_list = list(recv.unbind(0)) if (use_nccl and recv is not None) else None
     comm_stream = torch.cuda.Stream(device=dev)
     main_stream = torch.cuda.current_stream()
     moments_done = torch.cuda.Event()
+    fused_done = torch.cuda.Event()
+    push_done = torch.cuda.Event()
     gather_done = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"k": 0, "pending": None}
 
@@ -472,6 +484,15 @@ def run_b200(args):
             return
         k = state["k"]
         graph_moments.replay() if graph is not None else eng.run_moments()
+        if window is not None:
+            main_stream.wait_event(push_done)          # the previous step's copy has read eng.packed
+            graph_fused.replay() if graph is not None else eng.run_fused()
+            fused_done.record(main_stream)
+            comm_stream.wait_event(fused_done)
+            window.push(eng.packed, comm_stream)       # lands in rank 0's window under the next step's kernels
+            push_done.record(comm_stream)
+            state["k"] = k + 1
+            return
         if state["pending"] is not None:              # records of step k-1: gather them under this step's DP
             moments_done.record(main_stream)
             comm_stream.wait_event(moments_done)
@@ -483,14 +504,17 @@ def run_b200(args):
         state["k"] = k + 1
 
     def drain():
-        """Gather the records of the last step (nothing is left to overlap them with)."""
-        if world > 1 and state["pending"] is not None:
+        """The records of the last step (nothing is left to overlap them with)."""
+        if window is not None:
+            main_stream.wait_event(push_done)
+        elif world > 1 and state["pending"] is not None:
             moments_done.record(main_stream)
             comm_stream.wait_event(moments_done)
             launch_gather(state["pending"])
             main_stream.wait_event(gather_done[state["pending"]])
             state["pending"] = None
 
+    push_done.record(main_stream)
     for ev in gather_done:
         ev.record(main_stream)
     for _ in range(args.warmup):
@@ -544,7 +568,7 @@ def run_b200(args):
         w2.engine.run()
         torch.cuda.synchronize()
         shard_check = {"block": "rank %d's genes [%d, %d) recomputed on rank 0" % (world - 1, lo2, hi2),
-                       "records_identical": bool(torch.equal(w2.engine.packed, recv[world - 1]))}
+                       "records_identical": bool(torch.equal(w2.engine.packed, recv[world - 1][:w2.engine.packed.numel()]))}
         del w2
         torch.cuda.empty_cache()
 
@@ -595,8 +619,12 @@ def run_b200(args):
             "data": "synthetic",
             "config": config_dict(args.workload, args.dropout, world),     # identical in the reference arm
             "run": {"cuda_graph": graph is not None, "wall_s_timed_region": wall,
-                    "gather": ("NCCL gather of step k-1 on a side stream next to step k's fused fix-up / DP launch "
-                               "(two send buffers)") if world > 1 else "none"},
+                    "gather": "none" if world == 1 else (
+                        "peer copy: each rank writes its records into rank 0's peer-mapped window with one device-to-"
+                        "device copy over NVLink (copy engine, side stream), under the next step's kernels"
+                        if window is not None else
+                        "NCCL gather of step k-1 on a side stream next to step k's fused fix-up / DP launch "
+                        "(two send buffers)")},
             "e2e": {"value": G / e2e_t, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_t * 1e3, "steps": len(e2e_ms),
                     "ms_each": [round(v, 3) for v in e2e_ms],

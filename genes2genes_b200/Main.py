@@ -680,9 +680,12 @@ class RefQueryAligner:
                             self.TrajInt_R.interpolation_points, self.TrajInt_Q.interpolation_points,
                             self.state_params, self.device)
 
+    peer_gather = True   # use rank 0's peer-mapped window when the box allows it (else NCCL / gloo gather)
+
     def _gather_results(self):
-        """The one collective of the path: every rank's packed per-gene records go to rank 0 (NCCL gather of
-        equally sized byte buffers laid out for the largest shard).  Returns rank 0's host arrays for ALL
+        """The one collective of the path: every rank's packed per-gene records go to rank 0 (equally sized
+        byte buffers laid out for the largest shard): peer copies into rank 0's window
+        (``distributed.PeerWindow``) on one box, an NCCL gather otherwise.  Returns rank 0's host arrays for ALL
         genes, the own block's on the other ranks."""
         import torch
         import torch.distributed as dist
@@ -696,12 +699,24 @@ class RefQueryAligner:
             send = eng.packed
         else:   # empty shard: join the collective with an all-zero buffer
             send = torch.zeros(max(n_bytes, 8), dtype=torch.uint8, device=self.device)
-        on_host = dist.get_backend() != "nccl"   # gloo (tests: several ranks on one GPU) gathers host buffers
-        if on_host:
+        window = D.peer_window(max(n_bytes, 8), self.device) if self.peer_gather else None
+        on_host = window is None and dist.get_backend() != "nccl"   # gloo without peer mapping: host buffers
+        recv = None
+        if window is not None:
+            # every rank copies its records into rank 0's window (one device-to-device copy over NVLink, no kernel);
+            # first barrier: rank 0 has read the previous batch out of the window, second: every slot has landed
+            dist.barrier()
+            window.push(send)
             torch.cuda.current_stream().synchronize()
-            send = send.cpu()
-        recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=send.device) if rank == 0 else None
-        dist.gather(send, list(recv.unbind(0)) if rank == 0 else None, dst=0)
+            dist.barrier()
+            if rank == 0:
+                recv = window.rows()
+        else:
+            if on_host:
+                torch.cuda.current_stream().synchronize()
+                send = send.cpu()
+            recv = torch.empty((world, send.numel()), dtype=torch.uint8, device=send.device) if rank == 0 else None
+            dist.gather(send, list(recv.unbind(0)) if rank == 0 else None, dst=0)
         if rank != 0:
             if eng is None:
                 empty = np.zeros(max(n_bytes, 8), dtype=np.uint8)
@@ -716,7 +731,7 @@ class RefQueryAligner:
             raw = recv.numpy()
         else:
             host_buf = _engine._take_pinned(recv.numel())
-            host_buf.copy_(recv.view(-1), non_blocking=True)
+            host_buf.copy_(recv.reshape(-1), non_blocking=True)
             torch.cuda.current_stream().synchronize()
             raw = host_buf.numpy().reshape(world, -1)
         segments = [(raw[r], c, held, lo) for r, (_, c, held, lo) in enumerate(segments)]

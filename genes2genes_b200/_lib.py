@@ -46,6 +46,10 @@ SIGNATURES = {
     "g2g_pack_csr": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_csr_to_csc_workspace_bytes": (c_sz, [c_i64, c_i64]),
     "g2g_csr_to_csc": (c_i32, [c_vp, c_vp, c_vp, c_i64, c_vp, c_vp, c_i64, c_vp, c_vp, c_vp, c_vp, c_sz, c_vp]),
+    "g2g_peer_window_create": (c_i32, [c_sz, ctypes.POINTER(c_vp), c_vp]),
+    "g2g_peer_window_open": (c_i32, [c_vp, ctypes.POINTER(c_vp)]),
+    "g2g_peer_window_close": (c_i32, [c_vp, c_i32]),
+    "g2g_peer_push": (c_i32, [c_vp, c_vp, c_sz, c_vp]),
     "g2g_upload_block": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_i64, c_i64, c_vp, c_i64, c_vp]),
     "g2g_scatter_rows": (c_i32, [c_vp, c_i64, c_i64, c_i64, c_vp, c_vp, c_vp, c_i64, c_vp]),
     "g2g_weights_workspace_bytes": (c_sz, [c_i64, c_i32]),

@@ -4,6 +4,7 @@
 // `adata[np.argsort(adata.obs['time'])]` (TimeSeriesPreprocessor.py:20) and the densification
 // `adata.X.todense()` (Main.py:232,238; TSP.py:28).
 #include "g2g_common.cuh"
+#include <cstring>
 
 namespace {
 
@@ -218,6 +219,44 @@ extern "C" int g2g_upload_block(const float* host_src, int64_t ld_src, int64_t r
   G2G_CUDA_TRY(cudaMemcpy2DAsync(dst, (size_t)ld_dst * sizeof(float), host_src + (size_t)row0 * ld_src + col0,
                                  (size_t)ld_src * sizeof(float), (size_t)n_cols * sizeof(float), (size_t)n_rows,
                                  cudaMemcpyHostToDevice, (cudaStream_t)stream));
+  return G2G_OK;
+}
+
+// ---- result window on the gathering rank, written by its peers over NVLink (copy engines, no kernel) ----
+extern "C" int g2g_peer_window_create(size_t bytes, void** ptr, void* handle64) {
+  G2G_REQUIRE(ptr && handle64 && bytes > 0, "bad arguments");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+  void* p = nullptr;
+  G2G_CUDA_TRY(cudaMalloc(&p, bytes));
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, p);
+  if (e != cudaSuccess) {
+    cudaFree(p);
+    G2G_CUDA_TRY(e);
+  }
+  memcpy(handle64, &h, sizeof(h));
+  *ptr = p;
+  return G2G_OK;
+}
+
+extern "C" int g2g_peer_window_open(const void* handle64, void** ptr) {
+  G2G_REQUIRE(ptr && handle64, "bad arguments");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle64, sizeof(h));
+  G2G_CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+  return G2G_OK;
+}
+
+extern "C" int g2g_peer_window_close(void* ptr, int32_t owner) {
+  if (!ptr) return G2G_OK;
+  if (owner) G2G_CUDA_TRY(cudaFree(ptr));
+  else G2G_CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+  return G2G_OK;
+}
+
+extern "C" int g2g_peer_push(void* dst, const void* src, size_t bytes, void* stream) {
+  G2G_REQUIRE(dst && src, "null pointer");
+  if (bytes) G2G_CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
   return G2G_OK;
 }
 

@@ -82,3 +82,102 @@ class ResultGather:
             return None
         tmpl = record_templates(n_genes_per_rank, n_bins)
         return [{k: v.cpu().numpy() for k, v in unpack_records(b, tmpl).items()} for b in self.recv]
+
+
+class _DevicePointer:
+    """Raw device memory as a torch tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, shape):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "|u1", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+class PeerWindow:
+    """Rank ``dst``'s receive window ``[world, slot_bytes]``, mapped into every rank of the box
+    (``g2g_peer_window_*``): a rank's packed result records reach their slot with ONE asynchronous
+    device-to-device copy over NVLink / NVSwitch, executed by a copy engine -- no kernel, so the gather of
+    batch k never takes SMs from the persistent interpolation kernel of batch k+1 (an NCCL gather does).
+
+    Collective constructor (every rank of the default group calls it); raises ``RuntimeError`` on every rank
+    when any rank cannot map the window (no peer access, ranks on different hosts): callers then use the
+    NCCL / gloo gather.  Ordering is the caller's: before ``push`` the window must be free (``dst`` has read
+    the previous contents), after it a stream synchronise + barrier tells ``dst`` that every slot has landed."""
+
+    def __init__(self, slot_bytes, device, dst=0):
+        import ctypes
+        from . import _lib
+        self.lib = _lib.load()
+        self.rank, self.world, self.dst = dist.get_rank(), dist.get_world_size(), dst
+        self.slot_bytes = (int(slot_bytes) + 255) // 256 * 256
+        self.device = torch.device(device)
+        self.ptr, self.owner = None, self.rank == dst
+        handle = ctypes.create_string_buffer(64)
+        ptr = ctypes.c_void_p()
+        error = None
+        payload = [None]
+        with torch.cuda.device(self.device):
+            if self.owner:
+                try:
+                    _lib.check(self.lib.g2g_peer_window_create(self.slot_bytes * self.world, ctypes.byref(ptr), handle),
+                               "g2g_peer_window_create")
+                    self.ptr = ptr.value
+                    payload = [handle.raw]
+                except Exception as exc:       # reported to every rank below
+                    error = repr(exc)
+            self._broadcast(payload, dst)
+            if not self.owner:
+                if payload[0] is None:
+                    error = "the gathering rank could not create the window"
+                else:
+                    try:
+                        _lib.check(self.lib.g2g_peer_window_open(payload[0], ctypes.byref(ptr)), "g2g_peer_window_open")
+                        self.ptr = ptr.value
+                    except Exception as exc:
+                        error = repr(exc)
+            errors = [None] * self.world
+            dist.all_gather_object(errors, error)
+        if any(e is not None for e in errors):
+            self.close()
+            raise RuntimeError("peer window unavailable: %s" % next(e for e in errors if e is not None))
+
+    @staticmethod
+    def _broadcast(payload, src):
+        dist.broadcast_object_list(payload, src=src)
+
+    def push(self, records, stream=None):
+        """Copy this rank's packed records (u8 device tensor) into its slot, asynchronously on ``stream``
+        (default: the current stream)."""
+        from . import _lib
+        n = records.numel() * records.element_size()
+        if n > self.slot_bytes:
+            raise ValueError("records (%d bytes) do not fit the window slot (%d)" % (n, self.slot_bytes))
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(self.lib.g2g_peer_push(self.ptr + self.rank * self.slot_bytes, records.data_ptr(), n, st.cuda_stream),
+                   "g2g_peer_push")
+
+    def rows(self):
+        """On ``dst``: the window as a ``[world, slot_bytes]`` u8 device tensor (a view, not a copy)."""
+        if not self.owner:
+            return None
+        return torch.as_tensor(_DevicePointer(self.ptr, (self.world, self.slot_bytes)), device=self.device)
+
+    def close(self):
+        if self.ptr is not None:
+            with torch.cuda.device(self.device):
+                self.lib.g2g_peer_window_close(self.ptr, 1 if self.owner else 0)
+            self.ptr = None
+
+
+_windows = {}
+
+
+def peer_window(slot_bytes, device):
+    """The process-wide window for records of ``slot_bytes`` (made on first use; ``None`` when the box cannot
+    map one -- the answer is the same on every rank).  Collective on first use."""
+    key = (int(slot_bytes), str(device), dist.get_world_size())
+    if key not in _windows:
+        try:
+            _windows[key] = PeerWindow(slot_bytes, device)
+        except RuntimeError:
+            _windows[key] = None
+    return _windows[key]

@@ -95,6 +95,20 @@ int g2g_csr_to_csc(const int64_t* indptr, const int32_t* indices, const float* d
                    int32_t* row_idx, float* values, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * g2g_peer_window_* / g2g_peer_push -- the gather of SURVEY.md section 8(e) (reference: the results list
+ * `align_all_pairs` fills, Main.py:452-455; here one record block per rank) without a kernel: the
+ * gathering rank creates a device window (create: cudaMalloc + an inter-process handle of 64 bytes), the
+ * other ranks of the box map it (open: peer access over NVLink / NVSwitch is enabled on first use), and
+ * every rank copies its packed records into its slot with one asynchronous device-to-device copy on
+ * `stream` (push).  The copy runs on a copy engine, so nothing competes with the persistent kernels of
+ * the next batch.  Ordering between ranks (window free / all pushes landed) is the caller's: a stream
+ * synchronise plus a barrier.  close: `owner` != 0 frees the window, 0 unmaps a peer's view. */
+int g2g_peer_window_create(size_t bytes, void** ptr, void* handle64);
+int g2g_peer_window_open(const void* handle64, void** ptr);
+int g2g_peer_window_close(void* ptr, int32_t owner);
+int g2g_peer_push(void* dst, const void* src, size_t bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * g2g_upload_block / g2g_scatter_rows -- the host->device leg of the same step, for a HOST matrix
  * (`adata.X`, row major f32, cells x all genes), pipelined by row chunk: only the column block
  * [col0, col0+n_cols) a rank needs crosses PCIe (one strided DMA per chunk, cudaMemcpy2DAsync; the

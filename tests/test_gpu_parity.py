@@ -380,7 +380,7 @@ import os, sys
 sys.path.insert(0, %r)
 import numpy as np, torch, torch.distributed as dist
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
-torch.cuda.set_device(0)                      # every rank on the one GPU; the gather goes through gloo
+torch.cuda.set_device(0)                      # every rank on the one GPU; gathers: peer window, then gloo
 dist.init_process_group("gloo")
 from genes2genes_b200 import Main, synthetic, distributed
 from genes2genes_b200.anndata_lite import AnnDataLite
@@ -392,12 +392,17 @@ for G, nr, nq, T in ((203, 1500, 1300, 14), (70, 900, 800, 50), (3, 400, 300, 14
     block = (AnnDataLite(np.ascontiguousarray(Xr[:, lo:hi]), tr, genes[lo:hi]),
              AnnDataLite(np.ascontiguousarray(Xq[:, lo:hi]), tq, genes[lo:hi]))
     hosts = []
-    for ar, aq in (full, block):
+    # (1) records gathered through rank 0's peer-mapped window (device-to-device copies), (2) through gloo
+    for peer, (ar, aq) in ((True, full), (True, block), (False, block)):
+        Main.RefQueryAligner.peer_gather = peer
         al = Main.RefQueryAligner(ar, aq, genes, T, verbose=False, distributed=True)
         al.align_all_pairs()
         hosts.append(al)
         if rank != 0:
             assert len(al.results) == hi - lo
+    Main.RefQueryAligner.peer_gather = True
+    windows = [w for w in distributed._windows.values()]
+    assert windows and all(w is not None for w in windows), "peer window not mapped on this box"
     if rank == 0:
         single = Main.RefQueryAligner(full[0], full[1], genes, T, verbose=False)
         single.align_all_pairs()
@@ -415,7 +420,7 @@ dist.destroy_process_group()
 @pytest.mark.parametrize("world", [2, 4])
 def test_sharded_api_equals_single_gpu_on_one_gpu(tmp_path, world):
     """The multi-GPU API path -- shard -> per-rank column block upload -> kernels -> gather -> rank-0 result
-    objects -- with all ranks on ONE GPU (gloo gather): byte-identical to the single-process run, with whole
+    objects -- with all ranks on ONE GPU (gather through rank 0's inter-process window and through gloo): byte-identical to the single-process run, with whole
     matrices or only the rank's gene block on every rank, T = 14 (FFMA2 kernel) and 50 (tensor-core kernel),
     and with fewer genes than ranks (empty shards)."""
     import subprocess
