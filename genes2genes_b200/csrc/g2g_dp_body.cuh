@@ -94,9 +94,9 @@ __device__ __forceinline__ double match_cost(double t_mu, double t_var, double t
 // honours cost_in and the dense dump pointers (verification, on-demand per-gene matrices).
 // LW lanes serve one gene: 32 in general; for short series (T + 1 <= 16 / 8 columns, B = 1) a warp
 // carries 2 / 4 genes in its half / quarter segments so fewer lanes idle.
-// The warp (threadIdx.x >> 5) of block blockIdx.x aligns genes [(block * kWarpsPerBlock + warp) * GPW, + GPW);
-// `smem_raw` is the block's dp_smem_per_warp(T) * kWarpsPerBlock * GPW bytes of shared memory.
-template <int B, bool FULL, int LW>
+// The warp (threadIdx.x >> 5) of block blockIdx.x aligns genes [(block * WPB + warp) * GPW, + GPW);
+// `smem_raw` is the block's dp_smem_per_warp(T) * WPB * GPW bytes of shared memory.
+template <int B, bool FULL, int LW, int WPB = kWarpsPerBlock>
 __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_raw) {
   constexpr int GPW = 32 / LW;  // genes per warp
   const int T = p.n_bins;
@@ -104,7 +104,7 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
   const int lane = (threadIdx.x & 31) % LW;       // lane inside this gene's segment
   const int sub = (threadIdx.x & 31) / LW;
   const int warp = threadIdx.x >> 5;
-  const long long g_first = ((long long)blockIdx.x * kWarpsPerBlock + warp) * GPW;
+  const long long g_first = ((long long)blockIdx.x * WPB + warp) * GPW;
   if (g_first >= p.n_genes) return;  // whole warp leaves together; no block-level barriers below
   const bool active = g_first + sub < p.n_genes;
   const long long g = active ? g_first + sub : g_first;   // idle segments shadow the first gene, stores masked

@@ -19,13 +19,18 @@ __host__ __device__ inline size_t totals_smem_bytes(int T, int genes_per_block) 
   return (size_t)2 * genes_per_block * ((size_t)(2 * T + 1) * sizeof(double) + (size_t)T * sizeof(int32_t));
 }
 
-// Block = one warp per gene of the block (GPC = kWarpsPerBlock * GPW warps): all of them add up the
-// split totals and finish one gene each; the first kWarpsPerBlock warps then align GPW genes each.
-template <int B, int LW>
-__global__ void __launch_bounds__(kWarpsPerBlock * (32 / LW) * 32) fixup_dp_kernel(const __grid_constant__ FusedParams q) {
+// Block = one warp per gene of the block (GPC = WPB * GPW warps): all of them add up the
+// split totals and finish one gene each; the first WPB warps then align GPW genes each.
+// WPB = kWarpsPerBlock (4) in general.  kWideBlockWarps (17) for two DP columns per lane: the DP needs 122
+// registers, i.e. 16 resident warps per SM in 4-warp blocks -- 2368 genes per wave on 148 SMs, so a 2500-gene
+// shard (C4 over 8 GPUs) pays a second, nearly empty wave.  One 17-warp block per SM (544 threads, capped at 96
+// registers by the scheduler that gets five of the warps; 96 bytes of spills) holds 17 x 148 = 2516 genes.
+constexpr int kWideBlockWarps = 17;
+template <int B, int LW, int WPB>
+__global__ void __launch_bounds__(WPB * (32 / LW) * 32) fixup_dp_kernel(const __grid_constant__ FusedParams q) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int GPW = 32 / LW;
-  constexpr int GPC = kWarpsPerBlock * GPW;   // genes per block = warps per block
+  constexpr int GPC = WPB * GPW;   // genes per block = warps per block
   constexpr int kThreads = GPC * 32;
   constexpr int kLoads = B == 1 ? 24 : 12;   // loads in flight per thread in the split reduction (register room)
   const int T = q.fix.n_bins;
@@ -51,32 +56,58 @@ __global__ void __launch_bounds__(kWarpsPerBlock * (32 / LW) * 32) fixup_dp_kern
   const int32_t* ti[2] = {tot_i, tot_i + (size_t)T * GPC};
   if (g0 + warp < q.fix.n_genes) fixup_gene<(B < kMaxChunks ? B : kMaxChunks)>(q.fix, tf, ti, GPC, warp, g0 + warp, lane);
   __syncthreads();   // trends are visible to the block; the DP scratch below reuses the totals' shared memory
-  if (warp < kWarpsPerBlock) dp_genes<B, false, LW>(q.dp, smem_raw);
+  if (warp < WPB) dp_genes<B, false, LW, WPB>(q.dp, smem_raw);
 }
 
-template <int B, int LW>
+template <int WPB, int GPW>
+size_t fused_smem_bytes(int T) {
+  size_t smem = dp_smem_per_warp(T) * WPB * GPW;
+  const size_t tot = totals_smem_bytes(T, WPB * GPW);
+  return tot > smem ? tot : smem;
+}
+
+template <int B, int LW, int WPB>
 int launch_fused_mode(const FusedParams& q, cudaStream_t stream) {
   constexpr int GPW = 32 / LW;
-  const int T = q.fix.n_bins;
-  size_t smem = dp_smem_per_warp(T) * kWarpsPerBlock * GPW;
-  const size_t tot = totals_smem_bytes(T, kWarpsPerBlock * GPW);
-  if (tot > smem) smem = tot;
+  const size_t smem = fused_smem_bytes<WPB, GPW>(q.fix.n_bins);
   if (smem > 48 * 1024) {
-    G2G_CUDA_TRY(cudaFuncSetAttribute(fixup_dp_kernel<B, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    G2G_CUDA_TRY(cudaFuncSetAttribute(fixup_dp_kernel<B, LW, WPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  const unsigned blocks = (unsigned)g2g_ceil_div(q.fix.n_genes, kWarpsPerBlock * GPW);
-  fixup_dp_kernel<B, LW><<<blocks, kWarpsPerBlock * GPW * 32, smem, stream>>>(q);
+  const unsigned blocks = (unsigned)g2g_ceil_div(q.fix.n_genes, WPB * GPW);
+  fixup_dp_kernel<B, LW, WPB><<<blocks, WPB * GPW * 32, smem, stream>>>(q);
   G2G_CUDA_TRY(cudaGetLastError());
   return G2G_OK;
+}
+
+// Two DP columns per lane: one 17-warp block per SM exactly when the launch fits one wave of those but not one
+// wave of the 4-warp blocks (16 x SMs < genes <= 17 x SMs).  Measured at T = 50 on 148 SMs: 2500 genes 0.184 ms
+// against 0.228 ms (the 4-warp blocks' second wave holds 132 genes and still lasts one whole DP, 0.09 ms); with
+// more waves the wide blocks lose (96 registers, five warps on one scheduler: 0.184 ms per wave of 2516 genes
+// against 0.139 ms per wave of 2368; 10 000 genes 0.685 against 0.586 ms).  A function of the launch's gene count
+// and the device only -- the records do not depend on the block shape (same per-gene arithmetic and order).
+inline bool wide_blocks_fit_one_wave(const FusedParams& q) {
+#ifdef G2G_DP_NARROW_BLOCKS
+  return false;   // profiling builds: always the 4-warp blocks
+#endif
+  const size_t smem = fused_smem_bytes<kWideBlockWarps, 1>(q.fix.n_bins);
+  int dev = 0, sms = 0, smem_max = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return false;
+  if (cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+  if (sms <= 0 || smem + 1024 > (size_t)smem_max) return false;
+  const long long narrow_wave = 4ll * kWarpsPerBlock * sms;   // 4 resident 4-warp blocks per SM (122 -> 128 registers)
+  const long long wide_wave = (long long)kWideBlockWarps * sms;
+  return q.fix.n_genes > narrow_wave && q.fix.n_genes <= wide_wave;
 }
 
 template <int B>
 int launch_fused(const FusedParams& q, cudaStream_t stream) {
   if (B == 1) {  // short series: several genes per warp, as in g2g_cost_dp
-    if (q.fix.n_bins + 1 <= 8) return launch_fused_mode<1, 8>(q, stream);
-    if (q.fix.n_bins + 1 <= 16) return launch_fused_mode<1, 16>(q, stream);
+    if (q.fix.n_bins + 1 <= 8) return launch_fused_mode<1, 8, kWarpsPerBlock>(q, stream);
+    if (q.fix.n_bins + 1 <= 16) return launch_fused_mode<1, 16, kWarpsPerBlock>(q, stream);
   }
-  return launch_fused_mode<B, 32>(q, stream);
+  if (B == 2 && wide_blocks_fit_one_wave(q)) return launch_fused_mode<2, 32, kWideBlockWarps>(q, stream);
+  return launch_fused_mode<B, 32, kWarpsPerBlock>(q, stream);
 }
 
 }  // namespace

@@ -21,7 +21,11 @@ ap.add_argument("--cells", type=int, default=100000)
 ap.add_argument("--bins", type=int, default=50)
 ap.add_argument("--moments", default="auto")
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--lib", default=None, help="another build of libg2g.so (profiling variants)")
 args = ap.parse_args()
+if args.lib:
+    from genes2genes_b200 import _lib
+    _lib.LIB_PATH = os.path.abspath(args.lib)
 dev = torch.device("cuda", 0)
 G, n, T = args.genes, args.cells, args.bins
 Xr, tr, Xq, tq, _ = synthetic.make_pair_device(G, n, n, dev, dropout=0.9, seed=100)
@@ -54,5 +58,9 @@ for _ in range(args.reps):
     eng.time_fused(a, b)
     torch.cuda.synchronize()
     fu.append(a.elapsed_time(b))
+import hashlib  # noqa: E402
+eng.run()
+torch.cuda.synchronize()
+print("records sha", hashlib.sha256(eng.packed.cpu().numpy().tobytes()).hexdigest()[:16])
 print("variant %s step ms %s k1 ms %s -> %.0f GB/s; fused ms %s" % (eng.variant, np.round(ms, 3), np.round(k1, 3),
                                                                     4.0 * 2 * n * G / (min(k1) * 1e-3) / 1e9, np.round(fu, 3)))

@@ -486,6 +486,28 @@ def test_large_shape_properties_T50():
     assert all(s == "M" * T for s, e in zip(strs, expressed) if e)
 
 
+@pytest.mark.parametrize("T", [50, 36])
+def test_fused_launch_block_shapes_give_identical_records(T):
+    """The fused fix-up / DP launch picks one 17-warp block per SM when the genes fit one wave of those but not
+    one wave of the 4-warp blocks (16 x SMs < genes <= 17 x SMs; csrc/g2g_fused.cu).  The same genes aligned in
+    a launch of either shape give byte-identical records, and a sample equals the oracle."""
+    torch = _torch()
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    G_wide, G_narrow = 17 * sms - 3, 16 * sms - 5
+    Xr, tr, Xq, tq, _ = synthetic.make_pair(G_wide, 700, 600, dropout=0.85, seed=5 + T)
+    wide = _engine_from_arrays(Xr, tr, Xq, tq, T).run().results_to_host()
+    narrow = _engine_from_arrays(np.ascontiguousarray(Xr[:, :G_narrow]), tr, np.ascontiguousarray(Xq[:, :G_narrow]),
+                                 tq, T).run().results_to_host()
+    for k in narrow:
+        assert np.array_equal(np.asarray(wide[k])[:G_narrow], narrow[k]), k
+    sel = np.array([0, 1, G_narrow - 1, G_narrow, G_wide - 1])
+    ref = o.align_batch(Xr[:, sel], Xq[:, sel], tr, tq, T)
+    got = _strings(wide)
+    for n, g in enumerate(sel):
+        assert o.canonical_gap_blocks(got[g]) == o.canonical_gap_blocks(ref["alignment_str"][n])
+    np.testing.assert_allclose(wide["opt_cost"][sel], ref["opt_cost"], rtol=5e-5)
+
+
 def _device_case(G, nr, nq, T, dev, moments, sel):
     """Engine on a device-generated dataset (genes2genes_b200.synthetic.make_pair_device) + host copies of the
     sampled gene columns for the oracle."""
