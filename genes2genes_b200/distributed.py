@@ -167,15 +167,28 @@ class PeerWindow:
                 self.lib.g2g_peer_window_close(self.ptr, 1 if self.owner else 0)
             self.ptr = None
 
+    def close_collective(self):
+        """Every rank calls this: the peers unmap their views before the owner frees the memory."""
+        if not self.owner:
+            self.close()
+        dist.barrier()
+        if self.owner:
+            self.close()
 
-_windows = {}
+
+_windows = {}          # insertion-ordered: (slot bytes, device, world) -> PeerWindow or None
+_MAX_WINDOWS = 2       # a process that aligns batches of many shapes keeps the two most recent windows
 
 
 def peer_window(slot_bytes, device):
     """The process-wide window for records of ``slot_bytes`` (made on first use; ``None`` when the box cannot
-    map one -- the answer is the same on every rank).  Collective on first use."""
+    map one -- the answer is the same on every rank).  Collective on first use: every rank must ask for the
+    same sequence of sizes (they do: the size is a function of the gene list and the bin count)."""
     key = (int(slot_bytes), str(device), dist.get_world_size())
     if key not in _windows:
+        live = [k for k, w in _windows.items() if w is not None]
+        if len(live) >= _MAX_WINDOWS:
+            _windows.pop(live[0]).close_collective()
         try:
             _windows[key] = PeerWindow(slot_bytes, device)
         except RuntimeError:
