@@ -635,7 +635,12 @@ class AlignmentEngine:
         cur.wait_event(self._ev_join)
         cur.wait_event(self._ev_join2)
         st = _stream()
+        probe = self._probe
+        if probe is not None:
+            probe[0].record()
         self._launch_moments(st)
+        if probe is not None:
+            probe[1].record()
         if with_dp is None:
             return 5 if self.sparse else 7
         if with_dp:
@@ -647,6 +652,8 @@ class AlignmentEngine:
                                              _ptr(self.trends), _ptr(self.nnz), _ptr(self.flags),
                                              _ptr(self.align_str), _ptr(self.align_len), _ptr(self.opt_cost),
                                              _ptr(self.l_states), st), "g2g_fixup_cost_dp")
+            if probe is not None:
+                probe[2].record()
             return 6 if self.sparse else 8  # 2 x (weights + its per-bin sums[, pilot]) + moments + fused fix-up / DP
         _lib.check(lib.g2g_fixup_trends(self._sides, _ptr(self.ref.sum_w), _ptr(self.query.sum_w), _ptr(self.points),
                                         _ptr(self.eps_mean), _ptr(self.eps_std), G, G, T, _ptr(self.musigma),
@@ -676,6 +683,17 @@ class AlignmentEngine:
                        "g2g_moments_mma")
         else:
             _lib.check(lib.g2g_moments(self._sides, 2, G, G, T, st), "g2g_moments")
+
+    _probe = None
+
+    def time_step(self, before_moments, after_moments, after_fused):
+        """One whole step (``run()``) with three CUDA events recorded on the current stream around the moments
+        launch and after the fused launch: the kernels' durations inside a step, not alone."""
+        self._probe = (before_moments, after_moments, after_fused)
+        try:
+            self.run_interpolation(with_dp=True)
+        finally:
+            self._probe = None
 
     def time_moments(self, start_event, end_event):
         """Launch K1 alone between two CUDA events on the current stream (roofline measurement;
