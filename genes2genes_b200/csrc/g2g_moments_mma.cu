@@ -224,14 +224,14 @@ __device__ __forceinline__ uint32_t cvt2_f16x2(unsigned long long v) {
   asm("{\n.reg .f32 flo, fhi;\nmov.b64 {flo, fhi}, %1;\ncvt.rn.f16x2.f32 %0, fhi, flo;\n}" : "=r"(r) : "l"(v));
   return r;
 }
-// packed f32 pair of MINUS an f16x2: the sign flip is one XOR on the pair, the two conversions write the
-// halves of the 64-bit result directly (no negations / moves on the f32 side)
-__device__ __forceinline__ unsigned long long neg_unpack2(uint32_t h) {
+// packed f32 pair (h.lo - v.lo, h.hi - v.hi) of an f16x2 h and a packed f32 pair v: two mixed-precision
+// subtractions (SASS FHADD, f16 operand read from its half of the register) -- no conversion, negation or move
+__device__ __forceinline__ unsigned long long half2_minus(uint32_t h, unsigned long long v) {
   unsigned long long r;
-  asm("{\n.reg .b16 lo, hi;\n.reg .f32 flo, fhi;\nmov.b32 {lo, hi}, %1;\ncvt.f32.f16 flo, lo;\ncvt.f32.f16 fhi, hi;\n"
-      "mov.b64 %0, {flo, fhi};\n}"
+  asm("{\n.reg .b16 lo, hi;\n.reg .f32 vlo, vhi, dlo, dhi;\nmov.b32 {lo, hi}, %1;\nmov.b64 {vlo, vhi}, %2;\n"
+      "sub.rn.f32.f16 dlo, lo, vlo;\nsub.rn.f32.f16 dhi, hi, vhi;\nmov.b64 %0, {dlo, dhi};\n}"
       : "=l"(r)
-      : "r"(h ^ 0x80008000u));
+      : "r"(h), "l"(v));
   return r;
 }
 __device__ __forceinline__ unsigned long long pack2_asm(float lo, float hi) {
@@ -239,10 +239,11 @@ __device__ __forceinline__ unsigned long long pack2_asm(float lo, float hi) {
   asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
   return r;
 }
-// hi / lo f16 split of a packed pair: hi = f16(v), lo = f16((v - hi) * 2048); (v - hi) is exact in f32
+// hi / lo f16 split of a packed pair: hi = f16(v), lo = f16((v - hi) * 2048), formed as (hi - v) * -2048;
+// (hi - v) is exact in f32
 __device__ __forceinline__ void split2(unsigned long long v, uint32_t& hi, uint32_t& lo) {
   hi = cvt2_f16x2(v);
-  lo = cvt2_f16x2(mul2(add2(v, neg_unpack2(hi)), pack2(kLoScale, kLoScale)));
+  lo = cvt2_f16x2(mul2(half2_minus(hi, v), pack2(-kLoScale, -kLoScale)));
 }
 #ifdef __CUDA_FTZ
 #error "g2g_moments_mma.cu must be compiled without -ftz=true / --use_fast_math: nonzero_flag() relies on f32 denormals"
