@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 lib = os.path.join(ROOT, "genes2genes_b200", "libg2g.so")
 out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 want = ["UTCHMMA", "UTCBAR", "LDTM", "STTM", "UTMALDG", "UBLKCP", "SYNCS", "FFMA2", "FADD2", "FMUL2", "FFMA", "DFMA", "DADD",
-        "F2FP", "HADD2", "SHFL", "USETMAXREG", "BAR", "ATOMS", "REDG", "LDS", "STS", "LDG", "STG", "LDL", "STL"]
+        "F2FP", "HADD2", "FHADD", "SHFL", "USETMAXREG", "BAR", "ATOMS", "REDG", "LDS", "STS", "LDG", "STG", "LDL", "STL"]
 counts = collections.OrderedDict()
 name = None
 for line in out.splitlines():
