@@ -222,6 +222,7 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
   const int n_steps = T + n_lanes - 1;
   double fin_best = 0.0;  // min over the five matrices at (T, T) and its state, set by the owning lane
   int fin_state = 0;
+#pragma unroll 2
   for (int s = 0; s < n_steps; ++s) {
     Five nbr = shfl_up5<LW>(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
     const int i = s - lane + 1;
@@ -288,8 +289,10 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
         left = cur;     // (i, j) is its left input
         up[b] = cur;
       }
-      nbr_prev = nbr;
     }
+    // unconditional: before a lane's first row the neighbour's value IS row 0 of the column to the left (what
+    // nbr_prev was initialised with), after its last row nobody reads it; lane 0 never uses either
+    nbr_prev = nbr;
   }
   __syncwarp();
 
