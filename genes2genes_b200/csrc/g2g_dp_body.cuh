@@ -222,7 +222,9 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
   const int n_steps = T + n_lanes - 1;
   double fin_best = 0.0;  // min over the five matrices at (T, T) and its state, set by the owning lane
   int fin_state = 0;
-#pragma unroll 2
+  // unrolled by two for one or two DP columns per lane: the rotation of the five-state values between steps becomes
+  // register renaming (B = 2: ~30 fewer moves per step); with more columns per lane it only costs registers
+#pragma unroll (B <= 2 ? 2 : 1)
   for (int s = 0; s < n_steps; ++s) {
     Five nbr = shfl_up5<LW>(up[B - 1]);  // left neighbour's last column, row i (it finished it last step)
     const int i = s - lane + 1;
