@@ -24,6 +24,15 @@ void g2g_set_error(const char* fmt, ...);
     }                                                            \
   } while (0)
 
+// In-kernel bounds checks of a debug build (`make debug`: -DG2G_DEBUG, device-side assert); nothing in the
+// shipped library.  compute-sanitizer is not available on the GPU pool, these are the substitute.
+#ifdef G2G_DEBUG
+#include <assert.h>
+#define G2G_DEVICE_ASSERT(cond) assert(cond)
+#else
+#define G2G_DEVICE_ASSERT(cond) ((void)0)
+#endif
+
 static inline int64_t g2g_round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
 static inline int64_t g2g_ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
 

@@ -268,6 +268,7 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
           best5(up[b], c, &p.trans[10], cur.v[2], av);
           best5_gap(left, &p.trans[15], cur.v[3], ad);
           best5_gap(up[b], &p.trans[20], cur.v[4], ai);
+          G2G_DEVICE_ASSERT(i >= 1 && i <= T && j >= 1 && j <= T && (am | aw | av | ad | ai) < 8);
           bp[(size_t)(i - 1) * T + (j - 1)] = (uint16_t)(am | (aw << 3) | (av << 6) | (ad << 9) | (ai << 12));
           lbest = cur.v[0];
           lstate = 0;
@@ -314,6 +315,7 @@ __device__ __forceinline__ void dp_genes(const DpParams& p, unsigned char* smem_
       else prev = (bp[(size_t)(i - 1) * T + (j - 1)] >> (3 * state)) & 7;
       if (i == 0) state = 3;
       if (j == 0 && i > 0) state = 4;
+      G2G_DEVICE_ASSERT(state >= 0 && state < 5 && i >= 0 && j >= 0);
       sbuf[cap - 1 - len] = (uint8_t)((0x494456574dULL >> (8 * state)) & 0xff);  // "MWVDI"[state]
       ++len;
       if (state == 0) { --i; --j; }

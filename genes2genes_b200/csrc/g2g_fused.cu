@@ -38,6 +38,7 @@ __global__ void __launch_bounds__(WPB * (32 / LW) * 32) fixup_dp_kernel(const __
   double* tot_f = reinterpret_cast<double*>(smem_raw);                  // [2][2T+1][GPC]
   int32_t* tot_i = reinterpret_cast<int32_t*>(tot_f + (size_t)2 * rows_f * GPC);  // [2][T][GPC]
   const long long g0 = (long long)blockIdx.x * GPC;
+  G2G_DEVICE_ASSERT(g0 < q.fix.n_genes && blockDim.x == kThreads);
 
   const int rows = rows_f + T;
   for (int idx = threadIdx.x; idx < 2 * rows * GPC; idx += kThreads) {

@@ -437,6 +437,7 @@ __global__ void __launch_bounds__(kThreads, 1) moments_mma_kernel(const __grid_c
       tc_fence_after();
       const MmaSide& s = p.side[it.side];
       const long long g = (long long)it.gt * kGT + q * 32 + lane;
+      G2G_DEVICE_ASSERT(it.split >= 0 && it.split < s.n_split && it.gt * kGT < p.g_stride + kGT);
       double* pf = s.part_f64 + (size_t)it.split * (2 * T + 1) * p.g_stride + g;
 #pragma unroll
       for (int j = 0; j < N; j += 8) {

@@ -134,6 +134,7 @@ __global__ void __launch_bounds__(kCscThreads) csc_fill_kernel(const CscParams p
       if (p.col_map) c = p.col_map[c];
       if (c >= 0) {
         const long long at = p.col_ptr[c] + pos[c];
+        G2G_DEVICE_ASSERT(c < p.n_genes && at >= p.col_ptr[c] && at < p.col_ptr[c + 1]);
         pos[c] += 1;                        // one entry per (row, column): no other thread touches pos[c] in this row
         p.row_idx[at] = (int)r;
         p.values[at] = p.data[k];
